@@ -1,0 +1,83 @@
+"""ctypes binding of ``libmeshrcnn_b200.so`` (the C ABI declared in ``include/meshrcnn_b200.h``).
+
+There is deliberately NO CPU fallback: if the CUDA library is missing or a tensor is not a CUDA tensor the call
+raises.  PyTorch is used only for device memory, streams and autograd bookkeeping.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmeshrcnn_b200.so")
+
+_C = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_longlong, "f": ctypes.c_float, "d": ctypes.c_double}
+
+# name -> (return code, argument codes).  Must list every symbol of include/meshrcnn_b200.h
+# (tests/test_abi.py cross-checks this table, the header and the built .so).
+SIGNATURES = {
+    "mrb_version": ("i", ""),
+    "mrb_last_error": ("s", ""),
+    "mrb_device_info": ("i", "ppp"),
+    "mrb_cubify_workspace_bytes": ("l", "iiii"),
+    "mrb_cubify_count": ("i", "piiiifppp"),
+    "mrb_cubify_emit": ("i", "iiiippllpppppppp"),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+def load():
+    """Loads (once) and returns the ctypes library.  Raises LibraryMissing if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise LibraryMissing(
+                "meshrcnn_b200: %s not found -- build it with `python -m meshrcnn_b200.build` "
+                "(there is no CPU / PyTorch fallback for the hot path)" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (ret, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = ctypes.c_char_p if ret == "s" else _C[ret]
+            fn.argtypes = [_C[a] for a in args]
+        if lib.mrb_version() != 100:
+            raise RuntimeError("meshrcnn_b200: library/header version mismatch")
+        _lib = lib
+    return _lib
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    """Raw device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("meshrcnn_b200: expected a CUDA tensor (no CPU fallback), got device %s" % t.device)
+    if not t.is_contiguous():
+        raise RuntimeError("meshrcnn_b200: internal error, non-contiguous tensor passed to the C ABI")
+    return t.data_ptr()
+
+
+def check(code: int, what: str = ""):
+    if code != 0:
+        msg = load().mrb_last_error()
+        raise RuntimeError("meshrcnn_b200 %s failed (code %d): %s" % (what, code, msg.decode() if msg else "?"))
+
+
+def call(name: str, *args):
+    """Calls an int-returning entry point with the current stream appended, raising on error."""
+    lib = load()
+    check(getattr(lib, name)(*args, stream_ptr()), name)
