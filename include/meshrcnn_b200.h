@@ -53,6 +53,105 @@ int mrb_cubify_emit(int B, int Z, int Y, int X, void* workspace, const long long
                     long long E, float* verts, long long* faces, long long* adj, int32_t* rowptr, int32_t* col32,
                     int32_t* vert_mesh, void* vert_aux, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Graph utilities.
+ * mrb_coo_to_csr: 2 x E int64 COO (any order) -> CSR rowptr[n+1] / col[E] (int32); transpose != 0 builds the CSR
+ *   of the transposed matrix.  Row-sorted input keeps its edge order (deterministic); otherwise edges of a row
+ *   are placed with an atomic cursor.  workspace: 2*(n+1)+2 int32.
+ * mrb_csr_gather_fwd: out[i,:] = act(self[i,:] + sum_{j in row i} nbr[col[j],:]); `self` may be NULL; relu != 0
+ *   applies max(.,0).  Replaces aggregate_neighbours (reference meshRCNN/utils.py:52-57) and, with self/relu,
+ *   the add + ReLU of GraphConv.forward (meshRCNN/layers.py:63-68).  The backward of the aggregation is the same
+ *   call on the transposed CSR.
+ * mrb_relu_mask: gz = gout * (act > 0)  (backward of the ReLU at layers.py:68).
+ * mrb_segment_ids: ids[i] = s such that offsets[s] <= i < offsets[s+1]  (vertex -> mesh map from v_index).
+ */
+int mrb_coo_to_csr(const long long* adj, long long E, int n, int transpose, int32_t* rowptr, int32_t* col,
+                   int32_t* workspace, void* stream);
+int mrb_csr_gather_fwd(const int32_t* rowptr, const int32_t* col, int n, const float* self, int ld_self,
+                       const float* nbr, int ld_nbr, int D, int relu, float* out, int ld_out, void* stream);
+int mrb_relu_mask(const float* gout, int ld_g, const float* act, int ld_a, int n, int D, float* gz, int ld_z,
+                  void* stream);
+int mrb_segment_ids(const int32_t* offsets, int nseg, int n, int32_t* ids, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Dense contraction  C = op(A) * op(B) + beta * C  (row-major fp32, exact fp32 accumulate on the CUDA cores).
+ * Replaces torch.mm / nn.Linear at reference meshRCNN/layers.py:54,57,93,155,230,255,335 and their autograd.
+ */
+int mrb_sgemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+              float beta, float* C, int ldc, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * VertexAlign -- replaces VertexAlign.forward / single_projection / project, reference meshRCNN/layers.py:521-613,
+ * with the reference's exact (non-bilinear) semantics: out[v,c] = fmap[img,c,x1,y1] * [x2>x1 && y2>y1].
+ *   fmap       n_img x C x Hm x Wm fp32 (NCHW, Hm == Wm)
+ *   pos        SV x 3;  vert_mesh[v] = mesh of vertex v;  mesh_info[mesh] = {image index, image H, image W}
+ *   out        SV x ld_out (this map's channels are written at out[v*ld_out + 0..C-1]; pass a column-offset pointer)
+ * Backward: gfmap[img,c,x1,y1] += gout[v,c] (atomic fp32); vertex positions receive no gradient (as in the
+ * reference, where the integer cast at layers.py:592 cuts the graph).
+ */
+int mrb_vert_align_fwd(const float* fmap, int n_img, int C, int Hm, int Wm, const float* pos, const int32_t* vert_mesh,
+                       const int32_t* mesh_info, int SV, float* out, int ld_out, void* stream);
+int mrb_vert_align_bwd(const float* gout, int ld_g, int n_img, int C, int Hm, int Wm, const float* pos,
+                       const int32_t* vert_mesh, const int32_t* mesh_info, int SV, float* gfmap, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Surface sampling -- replaces utils/mesh_sampling.py:6-57 (sample, surface_areas), utils/process.py:7-20
+ * (normalize_mesh) and the per-mesh loop of batched_mesh_sampling (meshRCNN/loss_functions.py:80-89).
+ * Packed batch: verts SV x 3, faces SF x 3 int64 per-mesh local ids, v_off / f_off int32 offsets (B+1 entries).
+ *   mrb_face_areas        areas[f] = |AB x AC| / 2
+ *   mrb_face_area_cdf     + inclusive per-mesh CDF in fp64
+ *   mrb_sample_points_fwd n points per mesh: face by inverse CDF of u (or injected face_idx, local ids), barycentric
+ *                         weights (1-sqrt(xi1), (1-xi2)sqrt(xi1), xi2 sqrt(xi1)); u/xi2/xi1 NULL => Philox(seed).
+ *                         Outputs: raw points, global face id, weights (saved for backward), normalised cloud and
+ *                         per-cloud stats (8 doubles: mean[3], factor, argmax row or -1).
+ *   mrb_sample_points_bwd gcloud -> gverts (accumulated with atomics; caller zero-fills)
+ */
+int mrb_face_areas(const float* verts, const long long* faces, const int32_t* v_off, const int32_t* f_off, int B,
+                   int max_faces, float* areas, void* stream);
+int mrb_face_area_cdf(const float* verts, const long long* faces, const int32_t* v_off, const int32_t* f_off, int B,
+                      int max_faces, float* areas, double* cdf, void* stream);
+int mrb_sample_points_fwd(const float* verts, const long long* faces, const int32_t* v_off, const int32_t* f_off,
+                          const double* cdf, int B, int n, const float* u, const long long* face_idx, const float* xi2,
+                          const float* xi1, unsigned long long seed, float* raw, int32_t* fidx_out, float* w_out,
+                          float* cloud, double* stats, void* stream);
+int mrb_normalize_cloud_fwd(const float* raw, int B, int n, float* cloud, double* stats, void* stream);
+int mrb_sample_points_bwd(const float* gcloud, const float* cloud, const double* stats, const int32_t* fidx,
+                          const float* w, const long long* faces, const int32_t* v_off, int B, int n, float* gverts,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Chamfer / k-NN -- replaces batched_point2point_distance (cross branch), batched_chamfer_distance and the topk of
+ * compute_normals, reference meshRCNN/loss_functions.py:93-102,141,207-220.  No B x P x Q matrix is formed.
+ *   mrb_knn_fwd     for each point of a (B x P x 3): squared distance + index of the nearest point of b (B x Q x 3)
+ *                   and, if k > 0 (k <= 16), the k nearest indices sorted by distance (ties: lower index first).
+ *   mrb_sum_scaled  out[0] = scale * sum(x[0..n))   (fp64 accumulation; acc = 1 double of scratch)
+ *   mrb_chamfer_bwd gradient of  *g_a * scale * sum_i |a_i - b_idx_a[i]|^2 + *g_b * scale * sum_j |a_idx_b[j] - b_j|^2
+ *                   accumulated into ga / gb (either may be NULL).
+ */
+int mrb_knn_fwd(const float* a, const float* b, int B, int P, int Q, int k, float* min_d, int32_t* min_i, int32_t* knn,
+                void* stream);
+int mrb_sum_scaled(const float* x, long long n, double scale, double* acc, float* out, void* stream);
+int mrb_chamfer_bwd(const float* a, const float* b, int B, int P, int Q, const int32_t* idx_a, const int32_t* idx_b,
+                    const float* g_a, const float* g_b, float scale, float* ga, float* gb, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Normals + normal / edge losses -- replaces compute_normals, batched_normal_distance and total_edge_length,
+ * reference meshRCNN/loss_functions.py:107-170,175-189 (incl. the S.cpu() -> symeig -> .to(device) round trip).
+ *   mrb_normals_fwd     normal[b,p] = row 0 of the (ascending, canonically signed) eigenvector matrix of the 3x3
+ *                       scatter matrix of pt[b, knn[b,p,:]]
+ *   mrb_normals_bwd     gn -> gpt (atomic accumulate)
+ *   mrb_normal_loss_fwd out2[0] = sum_i |na_i . nb_idx_a[i]|, out2[1] = sum_j |nb_j . na_idx_b[j]|
+ *   mrb_edge_loss_fwd   out[0] = mean over the E directed edges of |v_r - v_c|^2
+ */
+int mrb_normals_fwd(const float* pt, const int32_t* knn, int B, int P, int k, float* normals_out, void* stream);
+int mrb_normals_bwd(const float* pt, const int32_t* knn, int B, int P, int k, const float* gn, float* gpt, void* stream);
+int mrb_normal_loss_fwd(const float* na, const float* nb, int B, int P, int Q, const int32_t* idx_a, const int32_t* idx_b,
+                        double* acc2, float* out2, void* stream);
+int mrb_normal_loss_bwd(const float* na, const float* nb, int B, int P, int Q, const int32_t* idx_a, const int32_t* idx_b,
+                        const float* g0, const float* g1, float* gna, float* gnb, void* stream);
+int mrb_edge_loss_fwd(const float* pos, const long long* adj, long long E, double* acc, float* out, void* stream);
+int mrb_edge_loss_bwd(const float* pos, const long long* adj, long long E, const float* g, float* gpos, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,6 +5,7 @@ raises.  PyTorch is used only for device memory, streams and autograd bookkeepin
 """
 import ctypes
 import os
+import re
 import threading
 
 import torch
@@ -12,18 +13,44 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmeshrcnn_b200.so")
 
-_C = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_longlong, "f": ctypes.c_float, "d": ctypes.c_double}
+_C = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_longlong, "L": ctypes.c_ulonglong, "f": ctypes.c_float,
+      "d": ctypes.c_double}
 
-# name -> (return code, argument codes).  Must list every symbol of include/meshrcnn_b200.h
-# (tests/test_abi.py cross-checks this table, the header and the built .so).
-SIGNATURES = {
-    "mrb_version": ("i", ""),
-    "mrb_last_error": ("s", ""),
-    "mrb_device_info": ("i", "ppp"),
-    "mrb_cubify_workspace_bytes": ("l", "iiii"),
-    "mrb_cubify_count": ("i", "piiiifppp"),
-    "mrb_cubify_emit": ("i", "iiiippllpppppppp"),
-}
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "meshrcnn_b200.h")
+
+
+def parse_header(path: str = HEADER_PATH):
+    """name -> (return code, argument codes) for every prototype of include/meshrcnn_b200.h -- the header is the
+    single source of truth for the ctypes signatures (codes: p pointer, i int, l long long, L unsigned long long,
+    f float, d double, s const char*)."""
+    src = re.sub(r"/\*.*?\*/", "", open(path).read(), flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\n\s*((?:const\s+)?(?:unsigned\s+)?(?:long\s+long|int|char|void|float|double)\s*\*?)\s*"
+                         r"(mrb_\w+)\s*\(([^)]*)\)\s*;", src):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
+        codes = ""
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                if "*" in a:
+                    codes += "p"
+                elif a.startswith("unsigned long long"):
+                    codes += "L"
+                elif a.startswith("long long"):
+                    codes += "l"
+                elif a.startswith("int"):
+                    codes += "i"
+                elif a.startswith("float"):
+                    codes += "f"
+                elif a.startswith("double"):
+                    codes += "d"
+                else:
+                    raise RuntimeError("meshrcnn_b200: cannot parse argument %r of %s" % (a, name))
+        protos[name] = ("s" if "char" in ret else ("l" if "long long" in ret else "i"), codes)
+    return protos
+
+
+SIGNATURES = parse_header()
 
 _lib = None
 _lock = threading.Lock()

@@ -1,0 +1,128 @@
+// Generic fp32 GEMM on the CUDA cores (exact fp32 accumulate): C = op(A) * op(B) + beta * C, row-major.
+//
+// Used for the small / odd-shaped contractions of the refinement stages (128->3 heads, K = 3 position columns,
+// weight gradients) and as the always-available exact-fp32 path; the N = 128/256 GraphConv projections run on the
+// tcgen05 tensor cores (gemm_tc.cu).  Replaces the torch.mm / nn.Linear call sites at reference
+// meshRCNN/layers.py:54,57,93,155,230,255,335.
+//
+// 64x64 tile, BK = 16, 256 threads, 4x4 register micro-tile; split-K over gridDim.z with fp32 atomics for the
+// tall-skinny weight-gradient shape (K = number of vertices).
+#include "common.cuh"
+#include "../../include/meshrcnn_b200.h"
+
+namespace mrb {
+namespace gemm {
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) k_sgemm(int M, int N, int K, const float* __restrict__ A, int lda,
+                                               const float* __restrict__ B, int ldb, float beta, float* __restrict__ C,
+                                               int ldc, int k_per_split, int atomic_out) {
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kbeg = blockIdx.z * k_per_split;
+    const int kend = min(K, kbeg + k_per_split);
+    const int tx = tid & 15, ty = tid >> 4;   // 16 x 16 threads, each 4 x 4 outputs
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+        // A tile: BM x BK  (element (m,k): TA ? A[k*lda+m] : A[m*lda+k])
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int idx = tid + r * 256;   // 0..1023
+            int m, k;
+            if (TA) { m = idx & 63; k = idx >> 6; } else { k = idx & 15; m = idx >> 4; }
+            const int gm = m0 + m, gk = k0 + k;
+            float v = 0.f;
+            if (gm < M && gk < kend) v = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+            As[k][m] = v;
+        }
+        // B tile: BK x BN  (element (k,n): TB ? B[n*ldb+k] : B[k*ldb+n])
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int idx = tid + r * 256;
+            int n, k;
+            if (TB) { k = idx & 15; n = idx >> 4; } else { n = idx & 63; k = idx >> 6; }
+            const int gn = n0 + n, gk = k0 + k;
+            float v = 0.f;
+            if (gn < N && gk < kend) v = TB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
+            Bs[k][n] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + ty * 4 + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + tx * 4 + j;
+            if (gn >= N) continue;
+            float* c = C + (size_t)gm * ldc + gn;
+            if (atomic_out) atomicAdd(c, acc[i][j]);
+            else *c = (beta == 0.f) ? acc[i][j] : fmaf(beta, *c, acc[i][j]);
+        }
+    }
+}
+
+__global__ void k_scale_rows(float* __restrict__ C, int M, int N, int ldc, float beta) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)M * N) return;
+    float* c = C + (size_t)(t / N) * ldc + (t % N);
+    *c = (beta == 0.f) ? 0.f : *c * beta;
+}
+
+}  // namespace gemm
+}  // namespace mrb
+
+using namespace mrb;
+using namespace mrb::gemm;
+
+extern "C" int mrb_sgemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                         float beta, float* C, int ldc, void* stream_) {
+    MRB_REQUIRE(A && B && C, "sgemm: null pointer");
+    MRB_REQUIRE(M >= 0 && N >= 0 && K >= 0, "sgemm: negative dimension");
+    if (M == 0 || N == 0) return MRB_OK;
+    cudaStream_t s = (cudaStream_t)stream_;
+    const int gx = ceil_div(N, BN), gy = ceil_div(M, BM);
+    // split-K when the output tile grid cannot fill the machine and K is long (weight gradients: K = #vertices)
+    int splits = 1;
+    if (K >= 4096 && gx * gy < 2 * kNumSMs) {
+        splits = min(ceil_div(4 * kNumSMs, gx * gy), ceil_div(K, 512));
+        if (splits < 1) splits = 1;
+    }
+    int kps = ceil_div(ceil_div(K, splits), BK) * BK;
+    if (kps == 0) kps = BK;
+    splits = K > 0 ? ceil_div(K, kps) : 1;
+    const int atomic_out = splits > 1;
+    if (atomic_out || K == 0) {
+        k_scale_rows<<<(unsigned)ceil_div64((long long)M * N, 256), 256, 0, s>>>(C, M, N, ldc, beta);
+        if (K == 0) return check_launch("sgemm");
+    }
+    dim3 grid(gx, gy, splits);
+#define LAUNCH(TA, TB) k_sgemm<TA, TB><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, beta, C, ldc, kps, atomic_out)
+    if (transA) { if (transB) LAUNCH(true, true); else LAUNCH(true, false); }
+    else { if (transB) LAUNCH(false, true); else LAUNCH(false, false); }
+#undef LAUNCH
+    return check_launch("sgemm");
+}

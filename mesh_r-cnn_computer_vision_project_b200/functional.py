@@ -64,3 +64,475 @@ def cubify(t: Tensor, threshold: float):
     topo = MeshTopology(SV, E, rowptr, col32, symmetric=True, vert_mesh=vert_mesh)
     register(adj, topo)
     return verts, v_counts[:last], faces, f_counts[:last], adj, topo
+
+
+# ----------------------------------------------------------------------------------------------------------
+# small cached host -> device tables (mesh offsets, per-mesh image records)
+# ----------------------------------------------------------------------------------------------------------
+_TABLE_CACHE = {}
+
+
+def _device_table(key, values, device) -> Tensor:
+    k = (key, tuple(values), str(device))
+    t = _TABLE_CACHE.get(k)
+    if t is None:
+        if len(_TABLE_CACHE) > 256:
+            _TABLE_CACHE.clear()
+        t = torch.tensor(list(values), dtype=torch.int32).to(device)
+        _TABLE_CACHE[k] = t
+    return t
+
+
+def offsets_table(counts: Sequence[int], device) -> Tensor:
+    """int32 [len+1] exclusive offsets of a list of per-mesh counts (``v_index`` / ``f_index``)."""
+    off = [0]
+    for c in counts:
+        off.append(off[-1] + int(c))
+    return _device_table("off", off, device)
+
+
+def vertex_mesh_ids(v_index: Sequence[int], num_vertices: int, device, topo: Optional[MeshTopology] = None) -> Tensor:
+    if topo is not None and topo.vert_mesh is not None and topo.num_vertices == num_vertices:
+        return topo.vert_mesh
+    off = offsets_table(v_index, device)
+    ids = torch.empty(num_vertices, dtype=torch.int32, device=device)
+    _lib.call("mrb_segment_ids", _lib.ptr(off), len(v_index), num_vertices, _lib.ptr(ids))
+    return ids
+
+
+def mesh_info_table(mesh_index: Sequence[int], image_sizes, device) -> Tensor:
+    """int32 [n_meshes, 3] = (image index, image H, image W) per mesh (reference layers.py:538-543)."""
+    rows = []
+    for img, (n_mesh, size) in enumerate(zip(mesh_index, image_sizes)):
+        H, W = int(size[0]), int(size[1])
+        for _ in range(int(n_mesh)):
+            rows += [img, H, W]
+    return _device_table("info", rows, device)
+
+
+def _f32c(t: Tensor) -> Tensor:
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# dense contraction on the library's GEMM
+# ----------------------------------------------------------------------------------------------------------
+def _gemm(ta: bool, tb: bool, M: int, N: int, K: int, a_ptr: int, lda: int, b_ptr: int, ldb: int, beta: float,
+          c_ptr: int, ldc: int) -> None:
+    _lib.call("mrb_sgemm", int(ta), int(tb), M, N, K, a_ptr, lda, b_ptr, ldb, float(beta), c_ptr, ldc)
+
+
+class _MatMul(torch.autograd.Function):
+    """y = x @ (w^T if trans_w else w)."""
+
+    @staticmethod
+    def forward(ctx, x, w, trans_w):
+        _require_cuda(x, "matmul")
+        x, w = _f32c(x), _f32c(w)
+        M, K = x.shape
+        N = w.shape[0] if trans_w else w.shape[1]
+        y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+        _gemm(False, trans_w, M, N, K, _lib.ptr(x), K, _lib.ptr(w), w.shape[1], 0.0, _lib.ptr(y), N)
+        ctx.save_for_backward(x, w)
+        ctx.trans_w = trans_w
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gy = _f32c(gy)
+        M, K = x.shape
+        N = gy.shape[1]
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            # gx = gy @ w (trans_w) or gy @ w^T
+            _gemm(False, not ctx.trans_w, M, K, N, _lib.ptr(gy), N, _lib.ptr(w), w.shape[1], 0.0, _lib.ptr(gx), K)
+        if ctx.needs_input_grad[1]:
+            gw = torch.empty_like(w)
+            if ctx.trans_w:   # w: N x K ; gw = gy^T @ x
+                _gemm(True, False, N, K, M, _lib.ptr(gy), N, _lib.ptr(x), K, 0.0, _lib.ptr(gw), K)
+            else:             # w: K x N ; gw = x^T @ gy
+                _gemm(True, False, K, N, M, _lib.ptr(x), K, _lib.ptr(gy), N, 0.0, _lib.ptr(gw), N)
+        return gx, gw, None
+
+
+def linear(x: Tensor, weight: Tensor) -> Tensor:
+    """nn.Linear(bias=False): x @ weight^T with weight stored out x in."""
+    return _MatMul.apply(x, weight, True)
+
+
+def matmul(x: Tensor, w: Tensor) -> Tensor:
+    return _MatMul.apply(x, w, False)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GraphConv
+# ----------------------------------------------------------------------------------------------------------
+def _gather(topo_rowptr, topo_col, n, self_ptr, ld_self, nbr_ptr, ld_nbr, D, relu, out_ptr, ld_out):
+    _lib.call("mrb_csr_gather_fwd", _lib.ptr(topo_rowptr), _lib.ptr(topo_col), n, self_ptr, ld_self, nbr_ptr, ld_nbr, D,
+              int(relu), out_ptr, ld_out)
+
+
+class _Aggregate(torch.autograd.Function):
+    """out[row] = sum over edges (row, col) of matrix[col]   (reference meshRCNN/utils.py:52-57)."""
+
+    @staticmethod
+    def forward(ctx, matrix, topo):
+        _require_cuda(matrix, "aggregate_neighbours")
+        m = _f32c(matrix)
+        n, D = m.shape
+        out = torch.empty_like(m)
+        _gather(topo.rowptr, topo.col, n, None, 0, _lib.ptr(m), D, D, False, _lib.ptr(out), D)
+        ctx.topo = topo
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _f32c(g)
+        n, D = g.shape
+        topo = ctx.topo
+        out = torch.empty_like(g)
+        _gather(topo.rowptr_t, topo.col_t, n, None, 0, _lib.ptr(g), D, D, False, _lib.ptr(out), D)
+        return out, None
+
+
+def aggregate_neighbours(index: Tensor, matrix: Tensor) -> Tensor:
+    return _Aggregate.apply(matrix, from_coo(index, matrix.shape[0]))
+
+
+class _GraphConv(torch.autograd.Function):
+    """relu(x W0 + A (x W1))  (reference meshRCNN/layers.py:47-68) as: one [x W0 | x W1] projection into a
+    n x 2D buffer, then one CSR gather with the add and the ReLU fused."""
+
+    @staticmethod
+    def forward(ctx, x, w0, w1, topo):
+        _require_cuda(x, "GraphConv")
+        x, w0, w1 = _f32c(x), _f32c(w0), _f32c(w1)
+        n, K = x.shape
+        D = w0.shape[1]
+        y = torch.empty(n, 2 * D, dtype=torch.float32, device=x.device)
+        yp = _lib.ptr(y)
+        _gemm(False, False, n, D, K, _lib.ptr(x), K, _lib.ptr(w0), D, 0.0, yp, 2 * D)
+        _gemm(False, False, n, D, K, _lib.ptr(x), K, _lib.ptr(w1), D, 0.0, yp + 4 * D, 2 * D)
+        out = torch.empty(n, D, dtype=torch.float32, device=x.device)
+        _gather(topo.rowptr, topo.col, n, yp, 2 * D, yp + 4 * D, 2 * D, D, True, _lib.ptr(out), D)
+        ctx.save_for_backward(x, w0, w1, out)
+        ctx.topo = topo
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, w0, w1, out = ctx.saved_tensors
+        topo = ctx.topo
+        gout = _f32c(gout)
+        n, K = x.shape
+        D = w0.shape[1]
+        gy = torch.empty(n, 2 * D, dtype=torch.float32, device=x.device)
+        gp = _lib.ptr(gy)
+        _lib.call("mrb_relu_mask", _lib.ptr(gout), D, _lib.ptr(out), D, n, D, gp, 2 * D)
+        _gather(topo.rowptr_t, topo.col_t, n, None, 0, gp, 2 * D, D, False, gp + 4 * D, 2 * D)
+        gx = gw0 = gw1 = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            _gemm(False, True, n, K, D, gp, 2 * D, _lib.ptr(w0), D, 0.0, _lib.ptr(gx), K)
+            _gemm(False, True, n, K, D, gp + 4 * D, 2 * D, _lib.ptr(w1), D, 1.0, _lib.ptr(gx), K)
+        if ctx.needs_input_grad[1]:
+            gw0 = torch.empty_like(w0)
+            _gemm(True, False, K, D, n, _lib.ptr(x), K, gp, 2 * D, 0.0, _lib.ptr(gw0), D)
+        if ctx.needs_input_grad[2]:
+            gw1 = torch.empty_like(w1)
+            _gemm(True, False, K, D, n, _lib.ptr(x), K, gp + 4 * D, 2 * D, 0.0, _lib.ptr(gw1), D)
+        return gx, gw0, gw1, None
+
+
+def graph_conv(x: Tensor, adj: Tensor, w0: Tensor, w1: Tensor) -> Tensor:
+    return _GraphConv.apply(x, w0, w1, from_coo(adj, x.shape[0]))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# VertexAlign
+# ----------------------------------------------------------------------------------------------------------
+class _VertAlign(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, vert_mesh, mesh_info, *fmaps):
+        _require_cuda(pos, "VertexAlign")
+        pos_c = _f32c(pos.detach())
+        maps = []
+        for f in fmaps:
+            _require_cuda(f, "VertexAlign")
+            if f.dim() != 4:
+                raise RuntimeError("VertexAlign: feature maps must be N x C x H x W")
+            maps.append(_f32c(f))
+        SV = pos_c.shape[0]
+        ctot = sum(m.shape[1] for m in maps)
+        out = torch.empty(SV, ctot, dtype=torch.float32, device=pos.device)
+        off = 0
+        for m in maps:
+            n_img, C, Hm, Wm = m.shape
+            _lib.call("mrb_vert_align_fwd", _lib.ptr(m), n_img, C, Hm, Wm, _lib.ptr(pos_c), _lib.ptr(vert_mesh),
+                      _lib.ptr(mesh_info), SV, _lib.ptr(out) + 4 * off, ctot)
+            off += C
+        ctx.save_for_backward(pos_c, vert_mesh, mesh_info)
+        ctx.shapes = [tuple(m.shape) for m in maps]
+        ctx.dtypes = [f.dtype for f in fmaps]
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        pos_c, vert_mesh, mesh_info = ctx.saved_tensors
+        gout = _f32c(gout)
+        SV, ctot = gout.shape
+        grads = []
+        off = 0
+        for i, shape in enumerate(ctx.shapes):
+            n_img, C, Hm, Wm = shape
+            if ctx.needs_input_grad[3 + i]:
+                g = torch.zeros(shape, dtype=torch.float32, device=gout.device)
+                _lib.call("mrb_vert_align_bwd", _lib.ptr(gout) + 4 * off, ctot, n_img, C, Hm, Wm, _lib.ptr(pos_c),
+                          _lib.ptr(vert_mesh), _lib.ptr(mesh_info), SV, _lib.ptr(g))
+                grads.append(g.to(ctx.dtypes[i]))
+            else:
+                grads.append(None)
+            off += C
+        return (None, None, None) + tuple(grads)   # no gradient to positions (reference layers.py:592)
+
+
+def vert_align(img_features: Sequence[Tensor], vertex_positions: Tensor, vertices_per_mesh: Sequence[int],
+               image_sizes, mesh_index: Sequence[int], topo: Optional[MeshTopology] = None) -> Tensor:
+    dev = vertex_positions.device
+    _require_cuda(vertex_positions, "VertexAlign")
+    if sum(int(m) for m in mesh_index) != len(vertices_per_mesh):
+        raise RuntimeError("VertexAlign: sum(mesh_index) must equal the number of meshes")
+    if sum(vertices_per_mesh) != vertex_positions.shape[0]:
+        raise RuntimeError("VertexAlign: vertices_per_mesh does not sum to the number of vertex positions")
+    vert_mesh = vertex_mesh_ids(vertices_per_mesh, vertex_positions.shape[0], dev, topo)
+    info = mesh_info_table(mesh_index, image_sizes, dev)
+    return _VertAlign.apply(vertex_positions, vert_mesh, info, *img_features)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# losses
+# ----------------------------------------------------------------------------------------------------------
+class _EdgeLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos, adj):
+        _require_cuda(pos, "edge loss")
+        pos_c = _f32c(pos)
+        adj_c = adj.contiguous()
+        if adj_c.dtype != torch.int64:
+            adj_c = adj_c.long()
+        E = adj_c.shape[1]
+        acc = torch.empty(1, dtype=torch.float64, device=pos.device)
+        out = torch.empty(1, dtype=torch.float32, device=pos.device)
+        _lib.call("mrb_edge_loss_fwd", _lib.ptr(pos_c), _lib.ptr(adj_c), E, _lib.ptr(acc), _lib.ptr(out))
+        ctx.save_for_backward(pos_c, adj_c)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        pos_c, adj_c = ctx.saved_tensors
+        gpos = torch.zeros_like(pos_c)
+        g = _f32c(g).reshape(1)
+        _lib.call("mrb_edge_loss_bwd", _lib.ptr(pos_c), _lib.ptr(adj_c), adj_c.shape[1], _lib.ptr(g), _lib.ptr(gpos))
+        return gpos, None
+
+
+def edge_length(pos: Tensor, adj: Tensor) -> Tensor:
+    """mean over the directed edge list of |v_r - v_c|^2 (reference loss_functions.py:47-48,175-189), O(E)."""
+    return _EdgeLoss.apply(pos, adj)
+
+
+def face_areas(verts: Tensor, faces: Tensor, v_index: Sequence[int], f_index: Sequence[int]) -> Tensor:
+    _require_cuda(verts, "surface_areas")
+    dev = verts.device
+    v = _f32c(verts.detach())
+    f = faces.contiguous().long()
+    areas = torch.empty(f.shape[0], dtype=torch.float32, device=dev)
+    if f.shape[0]:
+        _lib.call("mrb_face_areas", _lib.ptr(v), _lib.ptr(f), _lib.ptr(offsets_table(v_index, dev)),
+                  _lib.ptr(offsets_table(f_index, dev)), len(f_index), max(f_index), _lib.ptr(areas))
+    return areas
+
+
+class _Sample(torch.autograd.Function):
+    """Packed-batch surface sampling + unit-ball normalisation (mesh_sampling.py:6-35, process.py:7-20)."""
+
+    @staticmethod
+    def forward(ctx, verts, faces, v_off, f_off, B, max_faces, n, u, face_idx, xi2, xi1, seed):
+        _require_cuda(verts, "sample")
+        dev = verts.device
+        v = _f32c(verts)
+        f = faces.contiguous().long()
+        areas = torch.empty(f.shape[0], dtype=torch.float32, device=dev)
+        cdf = None
+        if face_idx is None:
+            cdf = torch.empty(f.shape[0], dtype=torch.float64, device=dev)
+            _lib.call("mrb_face_area_cdf", _lib.ptr(v), _lib.ptr(f), _lib.ptr(v_off), _lib.ptr(f_off), B, max_faces,
+                      _lib.ptr(areas), _lib.ptr(cdf))
+        raw = torch.empty(B, n, 3, dtype=torch.float32, device=dev)
+        cloud = torch.empty(B, n, 3, dtype=torch.float32, device=dev)
+        fidx = torch.empty(B, n, dtype=torch.int32, device=dev)
+        w = torch.empty(B, n, 3, dtype=torch.float32, device=dev)
+        stats = torch.empty(B, 8, dtype=torch.float64, device=dev)
+        cv = lambda t, dt: None if t is None else t.to(device=dev, dtype=dt).contiguous()
+        u, xi2, xi1 = cv(u, torch.float32), cv(xi2, torch.float32), cv(xi1, torch.float32)
+        face_idx = cv(face_idx, torch.int64)
+        _lib.call("mrb_sample_points_fwd", _lib.ptr(v), _lib.ptr(f), _lib.ptr(v_off), _lib.ptr(f_off), _lib.ptr(cdf), B, n,
+                  _lib.ptr(u), _lib.ptr(face_idx), _lib.ptr(xi2), _lib.ptr(xi1), int(seed), _lib.ptr(raw), _lib.ptr(fidx),
+                  _lib.ptr(w), _lib.ptr(cloud), _lib.ptr(stats))
+        ctx.save_for_backward(cloud, stats, fidx, w, f, v_off)
+        ctx.dims = (B, n, tuple(v.shape))
+        ctx.mark_non_differentiable(fidx)
+        return cloud, fidx
+
+    @staticmethod
+    def backward(ctx, gcloud, _gfidx):
+        cloud, stats, fidx, w, f, v_off = ctx.saved_tensors
+        B, n, vshape = ctx.dims
+        gverts = torch.zeros(vshape, dtype=torch.float32, device=cloud.device)
+        _lib.call("mrb_sample_points_bwd", _lib.ptr(_f32c(gcloud)), _lib.ptr(cloud), _lib.ptr(stats), _lib.ptr(fidx),
+                  _lib.ptr(w), _lib.ptr(f), _lib.ptr(v_off), B, n, _lib.ptr(gverts))
+        return (gverts,) + (None,) * 11
+
+
+def _next_seed() -> int:
+    # drawn from torch's CPU generator so that torch.manual_seed() makes sampling reproducible (no device sync)
+    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+
+
+def sample_points(verts: Tensor, faces: Tensor, v_index: Sequence[int], f_index: Sequence[int], n: int,
+                  u: Optional[Tensor] = None, face_idx: Optional[Tensor] = None, xi2: Optional[Tensor] = None,
+                  xi1: Optional[Tensor] = None, seed: Optional[int] = None) -> Tuple[Tensor, Tensor]:
+    """B x n x 3 normalised clouds (and the global face id of every point).  Randomness: Philox in-kernel from
+    ``seed`` (default: drawn from torch's generator), or injected ``u``/``face_idx`` + ``xi2`` + ``xi1`` (B x n)."""
+    dev = verts.device
+    _require_cuda(verts, "sample")
+    B = len(f_index)
+    if len(v_index) != B:
+        raise RuntimeError("sample: v_index and f_index must have the same length")
+    if B and min(f_index) <= 0:
+        raise RuntimeError("sample: every mesh needs at least one face")
+    if sum(v_index) != verts.shape[0] or sum(f_index) != faces.shape[0]:
+        raise RuntimeError("sample: index lists do not match the packed tensors")
+    if seed is None:
+        seed = _next_seed() if xi2 is None else 0
+    return _Sample.apply(verts, faces, offsets_table(v_index, dev), offsets_table(f_index, dev), B,
+                         max(f_index) if B else 0, int(n), u, face_idx, xi2, xi1, seed)
+
+
+class _Chamfer(torch.autograd.Function):
+    """Both directions of the nearest-neighbour search (+ optional k-NN index sets) and the two chamfer sums."""
+
+    @staticmethod
+    def forward(ctx, p, q, k):
+        _require_cuda(p, "chamfer")
+        _require_cuda(q, "chamfer")
+        pc, qc = _f32c(p), _f32c(q)
+        B, P, _ = pc.shape
+        Q = qc.shape[1]
+        dev = p.device
+        dp = torch.empty(B, P, dtype=torch.float32, device=dev)
+        dq = torch.empty(B, Q, dtype=torch.float32, device=dev)
+        ip = torch.empty(B, P, dtype=torch.int32, device=dev)
+        iq = torch.empty(B, Q, dtype=torch.int32, device=dev)
+        kp = torch.empty(B, P, k, dtype=torch.int32, device=dev) if k else None
+        kq = torch.empty(B, Q, k, dtype=torch.int32, device=dev) if k else None
+        _lib.call("mrb_knn_fwd", _lib.ptr(pc), _lib.ptr(qc), B, P, Q, k, _lib.ptr(dp), _lib.ptr(ip), _lib.ptr(kp))
+        _lib.call("mrb_knn_fwd", _lib.ptr(qc), _lib.ptr(pc), B, Q, P, k, _lib.ptr(dq), _lib.ptr(iq), _lib.ptr(kq))
+        acc = torch.empty(2, dtype=torch.float64, device=dev)
+        sums = torch.empty(2, dtype=torch.float32, device=dev)
+        _lib.call("mrb_sum_scaled", _lib.ptr(dp), B * P, 1.0, _lib.ptr(acc), _lib.ptr(sums))
+        _lib.call("mrb_sum_scaled", _lib.ptr(dq), B * Q, 1.0, _lib.ptr(acc) + 8, _lib.ptr(sums) + 4)
+        ctx.save_for_backward(pc, qc, ip, iq)
+        outs = [sums[0], sums[1], ip, iq]
+        ctx.mark_non_differentiable(ip, iq)
+        if k:
+            ctx.mark_non_differentiable(kp, kq)
+            outs += [kp, kq]
+        else:
+            outs += [None, None]
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, g1, g2, *_):
+        pc, qc, ip, iq = ctx.saved_tensors
+        B, P, _ = pc.shape
+        Q = qc.shape[1]
+        gp = torch.zeros_like(pc) if ctx.needs_input_grad[0] else None
+        gq = torch.zeros_like(qc) if ctx.needs_input_grad[1] else None
+        z = lambda g: torch.zeros(1, dtype=torch.float32, device=pc.device) if g is None else _f32c(g).reshape(1)
+        _lib.call("mrb_chamfer_bwd", _lib.ptr(pc), _lib.ptr(qc), B, P, Q, _lib.ptr(ip), _lib.ptr(iq), _lib.ptr(z(g1)),
+                  _lib.ptr(z(g2)), 1.0, _lib.ptr(gp), _lib.ptr(gq))
+        return gp, gq, None
+
+
+def chamfer_knn(p: Tensor, q: Tensor, k: int = 0):
+    """(loss_1, loss_2, idx_p, idx_q, knn_p, knn_q): loss_1 = sum_i min_j |p_i-q_j|^2, loss_2 the reverse direction
+    (reference loss_functions.py:93-102); idx_* int32 nearest indices; knn_* the k nearest indices (:141)."""
+    return _Chamfer.apply(p, q, int(k))
+
+
+class _NormalLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, q, knn_p, knn_q, idx_p, idx_q):
+        _require_cuda(p, "normal loss")
+        pc, qc = _f32c(p), _f32c(q)
+        B, P, _ = pc.shape
+        Q = qc.shape[1]
+        if P != Q:
+            # the reference gathers rows of a cloud with the *other* cloud's k-NN indices (loss_functions.py:141,146)
+            raise RuntimeError("normal loss requires equally sized clouds (reference semantics)")
+        k = knn_p.shape[2]
+        dev = p.device
+        i32 = lambda t: t.to(torch.int32).contiguous()
+        knn_p, knn_q, idx_p, idx_q = i32(knn_p), i32(knn_q), i32(idx_p), i32(idx_q)
+        n_p = torch.empty(B, P, 3, dtype=torch.float32, device=dev)
+        n_q = torch.empty(B, Q, 3, dtype=torch.float32, device=dev)
+        _lib.call("mrb_normals_fwd", _lib.ptr(pc), _lib.ptr(knn_p), B, P, k, _lib.ptr(n_p))
+        _lib.call("mrb_normals_fwd", _lib.ptr(qc), _lib.ptr(knn_q), B, Q, k, _lib.ptr(n_q))
+        acc = torch.empty(2, dtype=torch.float64, device=dev)
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        _lib.call("mrb_normal_loss_fwd", _lib.ptr(n_p), _lib.ptr(n_q), B, P, Q, _lib.ptr(idx_p), _lib.ptr(idx_q),
+                  _lib.ptr(acc), _lib.ptr(out))
+        ctx.save_for_backward(pc, qc, knn_p, knn_q, idx_p, idx_q, n_p, n_q)
+        return out[0], out[1]
+
+    @staticmethod
+    def backward(ctx, g0, g1):
+        pc, qc, knn_p, knn_q, idx_p, idx_q, n_p, n_q = ctx.saved_tensors
+        B, P, _ = pc.shape
+        Q = qc.shape[1]
+        k = knn_p.shape[2]
+        dev = pc.device
+        z = lambda g: torch.zeros(1, dtype=torch.float32, device=dev) if g is None else _f32c(g).reshape(1)
+        need_p, need_q = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gnp = torch.zeros_like(n_p) if need_p else None
+        gnq = torch.zeros_like(n_q) if need_q else None
+        _lib.call("mrb_normal_loss_bwd", _lib.ptr(n_p), _lib.ptr(n_q), B, P, Q, _lib.ptr(idx_p), _lib.ptr(idx_q),
+                  _lib.ptr(z(g0)), _lib.ptr(z(g1)), _lib.ptr(gnp), _lib.ptr(gnq))
+        gp = gq = None
+        if need_p:
+            gp = torch.zeros_like(pc)
+            _lib.call("mrb_normals_bwd", _lib.ptr(pc), _lib.ptr(knn_p), B, P, k, _lib.ptr(gnp), _lib.ptr(gp))
+        if need_q:
+            gq = torch.zeros_like(qc)
+            _lib.call("mrb_normals_bwd", _lib.ptr(qc), _lib.ptr(knn_q), B, Q, k, _lib.ptr(gnq), _lib.ptr(gq))
+        return gp, gq, None, None, None, None
+
+
+def normal_distance(p: Tensor, q: Tensor, knn_p: Tensor, knn_q: Tensor, idx_p: Tensor, idx_q: Tensor):
+    return _NormalLoss.apply(p, q, knn_p, knn_q, idx_p, idx_q)
+
+
+@torch.no_grad()
+def compute_normals(pt: Tensor, knn: Tensor) -> Tensor:
+    _require_cuda(pt, "compute_normals")
+    pc = _f32c(pt)
+    B, P, _ = pc.shape
+    knn = knn.to(torch.int32).contiguous()
+    out = torch.empty(B, P, 3, dtype=torch.float32, device=pt.device)
+    _lib.call("mrb_normals_fwd", _lib.ptr(pc), _lib.ptr(knn), B, P, knn.shape[2], _lib.ptr(out))
+    return out

@@ -50,3 +50,169 @@ class Cubify(nn.Module):
     def forward(self, t: Tensor):
         verts, v_index, faces, f_index, adj, _ = F_.cubify(t, float(self.threshold))
         return verts, v_index, faces, f_index, adj
+
+
+class VertexAlign(nn.Module):
+    """Projects mesh vertices into the image plane and pools feature-map texels.
+
+    Mirrors reference ``VertexAlign.forward(img_features, vertex_positions, vertices_per_mesh, image_sizes,
+    mesh_index)`` (meshRCNN/layers.py:521-546) including its actual arithmetic (:557-611): fixed intrinsics
+    (248, 111.5), clamp to the image, nearest-floor texel with the H/W axes swapped, 0/1 mask, no gradient to the
+    positions.  Output: SV x sum(C_m)."""
+
+    def forward(self, img_features: List[Tensor], vertex_positions: Tensor, vertices_per_mesh: List[int],
+                image_sizes: List[Tuple[int, int]], mesh_index: List[int]) -> Tensor:
+        if self.training:                                       # layers.py:528-530
+            assert len(vertices_per_mesh) == len(image_sizes)
+            assert list(mesh_index) == [1 for _ in image_sizes]
+        assert len(mesh_index) == len(image_sizes)              # layers.py:532
+        return F_.vert_align(img_features, vertex_positions, vertices_per_mesh, image_sizes, mesh_index)
+
+
+class GraphConv(nn.Module):
+    """f'_i = ReLU(W0 f_i + sum_{j in N(i)} W1 f_j)  -- reference meshRCNN/layers.py:25-68.
+    Parameters ``w0`` / ``w1`` are stored in x out and initialised U(+-1/sqrt(in)) (:42-45); no bias; the ReLU
+    is always applied (:68)."""
+
+    def __init__(self, in_features: int, out_features: int):
+        super().__init__()
+        self.w0 = nn.Parameter(torch.empty(in_features, out_features))
+        self.w1 = nn.Parameter(torch.empty(in_features, out_features))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        bound = 1.0 / math.sqrt(self.w0.size(0))
+        self.w0.data.uniform_(-bound, bound)
+        self.w1.data.uniform_(-bound, bound)
+
+    def forward(self, vertex_features: Tensor, vertex_adjacency: Tensor) -> Tensor:
+        return F_.graph_conv(vertex_features, vertex_adjacency, self.w0, self.w1)
+
+
+class _BiasFreeLinear(nn.Linear):
+    """``nn.Linear(bias=False)`` whose product runs on the library GEMM (same ``weight`` state-dict key)."""
+
+    def __init__(self, in_features: int, out_features: int):
+        super().__init__(in_features, out_features, bias=False)
+
+    def forward(self, x: Tensor) -> Tensor:
+        return F_.linear(x, self.weight)
+
+
+class ResGraphConv(nn.Module):
+    """Two GraphConvs plus an additive skip, linearly projected when the widths differ -- reference
+    meshRCNN/layers.py:71-100 (submodules ``conv0``, ``conv1``, ``projection``)."""
+
+    def __init__(self, in_features: int, out_features: int):
+        super().__init__()
+        self.conv0 = GraphConv(in_features, out_features)
+        self.conv1 = GraphConv(out_features, out_features)
+        self.projection = _BiasFreeLinear(in_features, out_features) if in_features != out_features else nn.Identity()
+
+    def forward(self, vertex_features: Tensor, vertex_adjacency: Tensor) -> Tensor:
+        skip = self.projection(vertex_features)
+        out = self.conv1(self.conv0(vertex_features, vertex_adjacency), vertex_adjacency)
+        return skip + out
+
+
+def _default_mesh_index(mesh_index, image_sizes):
+    return [1 for _ in image_sizes] if mesh_index is None else mesh_index
+
+
+def _stage_input(vertex_positions, pooled, vertex_features, use_input_features):
+    parts = [vertex_positions, pooled]
+    if vertex_features is not None:
+        assert use_input_features
+        parts = [vertex_features] + parts
+    else:
+        assert not use_input_features
+    return torch.cat(parts, dim=1)
+
+
+class ResVertixRefineShapenet(nn.Module):
+    """Residual ShapeNet refinement stage -- reference meshRCNN/layers.py:103-178.
+    NB the argument order of ``forward`` differs from the other two stage classes (:130-133)."""
+
+    def __init__(self, use_input_features: bool = True, num_features: int = 128, alignment_size: int = 3840,
+                 ndims: int = 3):
+        super().__init__()
+        self.vertAlign = VertexAlign()
+        self.linear = _BiasFreeLinear(alignment_size, num_features)
+        in_channels = num_features + ndims + (num_features if use_input_features else 0)
+        self.resGraphConv0 = ResGraphConv(in_channels, num_features)
+        self.use_input_features = use_input_features
+        self.resGraphConv1 = ResGraphConv(num_features, num_features)
+        self.resGraphConv2 = ResGraphConv(num_features, num_features)
+        self.graphConv = GraphConv(num_features, ndims)
+        self.tanh = nn.Tanh()
+
+    def forward(self, vertice_index: List[int], img_feature_maps: List[Tensor], vertex_adjacency: Tensor,
+                vertex_positions: Tensor, image_sizes: List, vertex_features: Optional[Tensor] = None,
+                mesh_index: List[int] = None) -> Tuple[Tensor, Tensor]:
+        mesh_index = _default_mesh_index(mesh_index, image_sizes)
+        aligned = self.vertAlign(img_feature_maps, vertex_positions, vertice_index, image_sizes, mesh_index)
+        projected = self.linear(aligned)
+        x = _stage_input(vertex_positions, projected, vertex_features, self.use_input_features)
+        x = self.resGraphConv0(x, vertex_adjacency)
+        x = self.resGraphConv1(x, vertex_adjacency)
+        x = self.resGraphConv2(x, vertex_adjacency)
+        delta = self.tanh(self.graphConv(x, vertex_adjacency))      # tanh(relu(.)): offsets >= 0 (:174-175)
+        return vertex_positions + delta, x
+
+
+class VertixRefineShapeNet(nn.Module):
+    """Plain ShapeNet refinement stage -- reference meshRCNN/layers.py:181-259."""
+
+    def __init__(self, use_input_features: bool = True, num_features: int = 128, alignment_size: int = 3840,
+                 ndims: int = 3):
+        super().__init__()
+        self.vertAlign = VertexAlign()
+        self.linear0 = _BiasFreeLinear(alignment_size, num_features)
+        in_channels = num_features + ndims + (num_features if use_input_features else 0)
+        self.graphConv0 = GraphConv(in_channels, num_features)
+        self.use_input_features = use_input_features
+        self.graphConv1 = GraphConv(num_features + ndims, num_features)
+        self.graphConv2 = GraphConv(num_features + ndims, num_features)
+        self.linear1 = _BiasFreeLinear(num_features, ndims)
+        self.tanh = nn.Tanh()
+
+    def forward(self, vertice_index: List[int], img_feature_maps: List[Tensor], vertex_adjacency: Tensor,
+                vertex_positions: Tensor, image_sizes: List, mesh_index: List[int] = None,
+                vertex_features: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+        mesh_index = _default_mesh_index(mesh_index, image_sizes)
+        aligned = self.vertAlign(img_feature_maps, vertex_positions, vertice_index, image_sizes, mesh_index)
+        projected = self.linear0(aligned)
+        x = _stage_input(vertex_positions, projected, vertex_features, self.use_input_features)
+        x = self.graphConv0(x, vertex_adjacency)
+        x = self.graphConv1(torch.cat([vertex_positions, x], dim=1), vertex_adjacency)
+        x = self.graphConv2(torch.cat([vertex_positions, x], dim=1), vertex_adjacency)
+        delta = self.tanh(self.linear1(x))
+        return vertex_positions + delta, x
+
+
+class VertixRefinePix3D(nn.Module):
+    """Pix3D refinement stage (single RoI feature map, no bottleneck) -- reference meshRCNN/layers.py:262-339."""
+
+    def __init__(self, use_input_features: bool = True, num_features: int = 128, alignment_size: int = 256,
+                 ndims: int = 3):
+        super().__init__()
+        self.vertAlign = VertexAlign()
+        in_channels = alignment_size + ndims + (num_features if use_input_features else 0)
+        self.graphConv0 = GraphConv(in_channels, num_features)
+        self.use_input_features = use_input_features
+        self.graphConv1 = GraphConv(num_features + ndims, num_features)
+        self.graphConv2 = GraphConv(num_features + ndims, num_features)
+        self.linear = _BiasFreeLinear(num_features + ndims, ndims)
+        self.tanh = nn.Tanh()
+
+    def forward(self, vertice_index: List[int], back_bone_features: Tensor, vertex_adjacency: Tensor,
+                vertex_positions: Tensor, image_sizes: List, mesh_index: List[int] = None,
+                vertex_features: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+        mesh_index = _default_mesh_index(mesh_index, image_sizes)
+        aligned = self.vertAlign([back_bone_features], vertex_positions, vertice_index, image_sizes, mesh_index)
+        x = _stage_input(vertex_positions, aligned, vertex_features, self.use_input_features)
+        x = self.graphConv0(x, vertex_adjacency)
+        x = self.graphConv1(torch.cat([vertex_positions, x], dim=1), vertex_adjacency)
+        x = self.graphConv2(torch.cat([vertex_positions, x], dim=1), vertex_adjacency)
+        delta = self.tanh(self.linear(torch.cat([vertex_positions, x], dim=1)))
+        return vertex_positions + delta, x

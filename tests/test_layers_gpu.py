@@ -1,0 +1,213 @@
+"""VertexAlign / GraphConv / refinement stages: CUDA path vs the reference's outputs (tests/golden, produced by
+oracle/make_golden.py from the unmodified reference) and vs the oracle on fresh seeded inputs.
+Tolerance (north star): fp32 rtol 1e-4 on values and gradients; VertexAlign is a pure gather -> bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cubify_np, mesh_ops
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def cuda(x, grad=False):
+    t = torch.as_tensor(np.asarray(x)).cuda()
+    if t.is_floating_point():
+        t = t.float()
+    return t.requires_grad_() if grad else t
+
+
+def close(got, want, rtol=RTOL, atol=None, what=""):
+    want = torch.as_tensor(np.asarray(want)).double()
+    got = got.detach().cpu().double()
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    if atol is None:
+        atol = rtol * float(want.abs().max()) * 1e-1 + 1e-30     # gradients span decades: scale atol to the tensor
+    err = (got - want).abs()
+    tol = atol + rtol * want.abs()
+    assert bool((err <= tol).all()), "%s: max err %.3e (tol %.3e), max|want| %.3e" % (
+        what, float(err.max()), float(tol.min()), float(want.abs().max()))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,nmaps", [("pix", 1), ("shp", 4), ("randint", 2), ("border", 1)])
+def test_vert_align_matches_reference_bit_exact(lib, golden, name, nmaps):
+    from meshrcnn_b200.layers import VertexAlign
+    g = golden("vert_align")
+    hw = int(g[name + "__hw"])
+    fm = [cuda(g["%s__fm%d" % (name, i)], grad=True) for i in range(nmaps)]
+    pos = cuda(g[name + "__pos"], grad=True)
+    vpm = g[name + "__vpm"].tolist()
+    out = VertexAlign().eval()(fm, pos, vpm, [(hw, hw)] * 3, [1, 1, 1])
+    want = g[name + "_f32__out"]
+    assert out.dtype == torch.float32
+    assert np.array_equal(out.detach().cpu().numpy(), want), "VertexAlign not bit-exact"
+    if name in ("pix", "shp"):
+        assert float((torch.as_tensor(want) != 0).float().mean()) > 0.5     # the gather is really exercised
+    (out * cuda(g[name + "_f64__gout"])).sum().backward()
+    assert pos.grad is None                                                 # reference: no gradient to positions
+    for i in range(nmaps):
+        close(fm[i].grad, g["%s_f64__gfm%d" % (name, i)], what="gfm%d" % i)
+
+
+def test_vert_align_mesh_index_and_errors(lib):
+    """Several meshes per image (eval path, layers.py:538-543) against the oracle."""
+    from meshrcnn_b200 import synthetic
+    from meshrcnn_b200.layers import VertexAlign
+    fm = synthetic.feature_maps(2, [(8, 12, 12)], 3)
+    pos = synthetic.in_frustum_positions(90, 224, 4)
+    vpm, mi, sizes = [20, 30, 40], [2, 1], [(224, 224), (224, 224)]
+    want = mesh_ops.vert_align(fm, pos, vpm, sizes, mi)
+    got = VertexAlign().eval()([f.cuda() for f in fm], pos.cuda(), vpm, sizes, mi)
+    assert torch.equal(got.cpu(), want)
+    with pytest.raises(RuntimeError):
+        VertexAlign().eval()([f.cuda() for f in fm], pos.cuda(), [20, 30], sizes, mi)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def test_aggregate_known_answer(lib):
+    """reference tests/test_layers.py:16-26 (non-symmetric, unsorted-by-row-safe COO)."""
+    from meshrcnn_b200.utils import aggregate_neighbours
+    a = torch.tensor([[1., 2, 3], [4, 5, 6], [7, 8, 9]]).cuda()
+    ei = torch.tensor([[0, 0, 1, 2], [1, 2, 1, 0]]).cuda()
+    out = aggregate_neighbours(ei, a)
+    assert torch.allclose(out.cpu(), torch.tensor([[11., 13, 15], [4, 5, 6], [1, 2, 3]]))
+
+
+def test_aggregate_unsorted_coo_and_grad(lib):
+    from meshrcnn_b200.utils import aggregate_neighbours
+    g = torch.Generator().manual_seed(0)
+    n, E, D = 50, 400, 7
+    ei = torch.randint(0, n, (2, E), generator=g)
+    m = torch.randn(n, D, generator=g)
+    mc = m.cuda().requires_grad_()
+    out = aggregate_neighbours(ei.cuda(), mc)
+    m64 = m.double().requires_grad_()
+    want = mesh_ops.aggregate_neighbours(ei, m64)
+    close(out, want.detach(), what="aggregate")
+    go = torch.randn(n, D, generator=g)
+    (out * go.cuda()).sum().backward()
+    (want * go.double()).sum().backward()
+    close(mc.grad, m64.grad, what="aggregate grad")
+
+
+def test_graphconv_known_answer(lib):
+    """reference tests/test_layers.py:58-74: all-ones weights on a path graph -> rows [15, 36, 33]."""
+    from meshrcnn_b200.layers import GraphConv
+    conv = GraphConv(3, 6).cuda()
+    with torch.no_grad():
+        conv.w0.fill_(1)
+        conv.w1.fill_(1)
+    x = torch.arange(9).reshape(3, 3).float().cuda()
+    adj = torch.tensor([[0, 1, 0], [1, 0, 1], [0, 1, 0]]).nonzero().t().contiguous().cuda()
+    out = conv(x, adj)
+    assert torch.allclose(out.cpu(), torch.tensor([15., 36, 33]).view(3, 1).expand(3, 6))
+
+
+@pytest.mark.parametrize("name", ["gc_19_16", "gc_16_3", "gc_35_24"])
+def test_graphconv_matches_reference(lib, golden, name):
+    from meshrcnn_b200.layers import GraphConv
+    g = golden("graphconv_stages")
+    w0 = g[name + "__w0"]
+    conv = GraphConv(*w0.shape).cuda()
+    conv.load_state_dict({"w0": torch.as_tensor(w0), "w1": torch.as_tensor(g[name + "__w1"])})
+    x = cuda(g[name + "__x"], grad=True)
+    adj = cuda(g["adj"]).long()
+    out = conv(x, adj)
+    close(out, g[name + "_f64__out"], what="out")
+    (out * cuda(g[name + "_f64__gout"])).sum().backward()
+    close(x.grad, g[name + "_f64__gx"], what="gx")
+    close(conv.w0.grad, g[name + "_f64__gw0"], what="gw0")
+    close(conv.w1.grad, g[name + "_f64__gw1"], what="gw1")
+
+
+@pytest.mark.parametrize("cls", ["ResVertixRefineShapenet", "VertixRefineShapeNet", "VertixRefinePix3D"])
+@pytest.mark.parametrize("use_feat", [0, 1])
+def test_stage_matches_reference(lib, golden, cls, use_feat):
+    """State-dict drop-in: the reference module's own state_dict is loaded into ours."""
+    import meshrcnn_b200.layers as L
+    g = golden("graphconv_stages")
+    tag = "%s_%d" % (cls, use_feat)
+    sd = {k[len(tag) + 6:]: torch.as_tensor(v) for k, v in g.items() if k.startswith(tag + "__sd__")}
+    nmaps = 1 if cls == "VertixRefinePix3D" else 4
+    fm = [cuda(g["%s__fm%d" % (cls, i)], grad=True) for i in range(nmaps)]
+    align_c = sum(f.shape[1] for f in fm)
+    mod = getattr(L, cls)(use_input_features=bool(use_feat), num_features=16, alignment_size=align_c).cuda().eval()
+    mod.load_state_dict(sd, strict=True)
+    hw = int(g[cls + "__hw"])
+    pos = cuda(g[cls + "__pos"], grad=True)
+    feats = cuda(g[cls + "__feats"], grad=True) if use_feat else None
+    adj = cuda(g["adj"]).long()
+    v_index = g["v_index"].tolist()
+    new_pos, new_feat = mod(v_index, fm[0] if nmaps == 1 else fm, adj, pos, [(hw, hw)] * 2, vertex_features=feats)
+    t64 = tag + "_f64"
+    close(new_pos, g[t64 + "__new_pos"], what="new_pos")
+    close(new_feat, g[t64 + "__new_feat"], what="new_feat")
+    ((new_pos * cuda(g[tag + "_f64__gpos_out"])).sum() + (new_feat * cuda(g[tag + "_f64__gfeat_out"])).sum()).backward()
+    close(pos.grad, g[t64 + "__grad__pos"], what="grad pos")
+    for i in range(nmaps):
+        close(fm[i].grad, g[t64 + "__grad__fm%d" % i], what="grad fm%d" % i)
+    if use_feat:
+        close(feats.grad, g[t64 + "__grad__feats"], what="grad feats")
+    for k, p in mod.named_parameters():
+        close(p.grad, g[t64 + "__grad__param__" + k], what="grad " + k)
+
+
+def test_stage_chain_on_cubified_batch_vs_oracle(lib):
+    """Cubify -> 3 Pix3D stages at production width (128 features, 256-channel 12x12 map), fwd + bwd vs the oracle in
+    fp64 (positions are in-frustum so the gather is exercised; the graph is the cubified one)."""
+    import meshrcnn_b200.layers as L
+    from meshrcnn_b200 import synthetic
+    B, V = 3, 12
+    vox = synthetic.blob_voxels(B, V, 0)
+    verts, v_index, faces, f_index, adj = L.Cubify(0.2)(vox.cuda())
+    o = cubify_np.cubify(vox.numpy(), 0.2)
+    assert np.array_equal(adj.cpu().numpy(), o[4])
+    SV = verts.shape[0]
+    torch.manual_seed(1)
+    stages = [L.VertixRefinePix3D(use_input_features=bool(i)).cuda() for i in range(3)]
+    with torch.no_grad():                      # default init + neighbour sums grow ~20x per layer and saturate the tanh
+        for st in stages:
+            for prm in st.parameters():
+                prm.mul_(0.2)
+    fmap = synthetic.feature_maps(B, [synthetic.PIX3D_MAP], 0)[0] * 0.02     # keeps the tanh heads unsaturated
+    pos0 = synthetic.in_frustum_positions(SV, 224, 5)
+    sizes = [(224, 224)] * B
+
+    fm_c = fmap.cuda().requires_grad_()
+    p = pos0.cuda().requires_grad_()
+    feats = None
+    cur = p
+    for st in stages:
+        cur, feats = st(v_index, fm_c, adj, cur, sizes, vertex_features=feats)
+    go_p = torch.randn(SV, 3, generator=torch.Generator().manual_seed(2))
+    (cur * go_p.cuda()).sum().backward()
+
+    def oracle(dt):
+        fm = fmap.to(dt).requires_grad_()
+        p_ = pos0.to(dt).requires_grad_()
+        params = [{k: v.detach().cpu().to(dt).requires_grad_() for k, v in st.named_parameters()} for st in stages]
+        c, f = p_, None
+        for sd in params:
+            c, f = mesh_ops.stage_pix3d(sd, v_index, fm, adj.cpu(), c, sizes, feats=f)
+        (c * go_p.to(dt)).sum().backward()
+        out = {"pos3": c.detach(), "feat3": f.detach(), "grad pos0": p_.grad, "grad fmap": fm.grad}
+        for i, sd in enumerate(params):
+            for k, v in sd.items():
+                out["grad %d.%s" % (i, k)] = v.grad
+        return out
+
+    o64, o32 = oracle(torch.float64), oracle(torch.float32)
+    got = {"pos3": cur, "feat3": feats, "grad pos0": p.grad, "grad fmap": fm_c.grad}
+    for i, st in enumerate(stages):
+        for k, prm in st.named_parameters():
+            got["grad %d.%s" % (i, k)] = prm.grad
+    # Deep fp32 chain: ReLU masks of pre-activations within one ulp of zero differ between any two fp32 evaluations, so
+    # the bound is rtol 1e-4 in relative L2 norm OR 3x the reference's own |fp32 - fp64| deviation, whichever is larger.
+    for name, want in o64.items():
+        w = want.double()
+        assert float(w.norm()) > 0, name
+        err = float((got[name].detach().cpu().double() - w).norm() / w.norm())
+        ref = float((o32[name].double() - w).norm() / w.norm())
+        assert err <= max(1e-4, 3 * ref), (name, err, ref)

@@ -1,0 +1,192 @@
+"""Sampling + chamfer / normal / edge losses: CUDA path vs the reference's outputs (tests/golden) and the fp64
+oracle.  Tolerances: fp32 rtol 1e-4 (north star); k-NN / NN index sets compared exactly away from fp32 ties.
+
+Normal loss: the reference takes a *row* of the eigenvector matrix, whose value depends on
+LAPACK's unspecified eigenvector signs; the kernel uses a documented canonical sign rule and is compared with the
+oracle under the same rule (``canonical_signs=True``); everything else (k-NN sets, scatter matrices, eigenvectors up
+to sign, backward) is compared directly."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mesh_ops
+from tests.test_layers_gpu import close, cuda
+
+pytestmark = pytest.mark.gpu
+
+
+class FakeBatch:
+    def __init__(self, meshes, vertice_index, face_index):
+        self.meshes, self.vertice_index, self.face_index = meshes, vertice_index, face_index
+
+
+def test_known_answers_from_reference_tests(lib):
+    """tests/test_loss_functions.py:14-55,59-72,76-96,100-125 of the reference, through the fused kernels."""
+    from meshrcnn_b200 import loss_functions as LF
+    from meshrcnn_b200.mesh_sampling import surface_areas, sample
+    from meshrcnn_b200.utils import dummy
+    # chamfer sums 300 / 21 and 600 / 42 (exact ==)
+    pt0, pt1 = dummy(1, 10, 3).cuda(), (dummy(1, 7, 3) + 1).cuda()
+    l0, i0, l1, i1 = LF.chamfer_distance(pt0, pt1)
+    assert i0.shape == (1, 10) and i1.shape == (1, 7) and l0.item() == 300 and l1.item() == 21
+    l0, i0, l1, i1 = LF.chamfer_distance(pt0.expand(2, 10, 3).contiguous(), pt1.expand(2, 7, 3).contiguous())
+    assert l0.item() == 600 and l1.item() == 42
+    d = LF.batched_point2point_distance(pt0, pt1)
+    r0, ri0, r1, ri1 = LF.batched_chamfer_distance(d)
+    assert r0.item() == 300 and r1.item() == 21 and torch.equal(ri0, i0[:1]) and torch.equal(ri1, i1[:1])
+    # edge length (test_edge_length)
+    pos = dummy(1, 10, 3).squeeze().cuda()
+    adj = torch.tensor([[0, 1, 1, 2], [1, 0, 2, 1]]).cuda()
+    p2p = LF.batched_point2point_distance(pos).squeeze()
+    want = (p2p[0, 1] + p2p[1, 0] + p2p[1, 2] + p2p[2, 1]) / 4
+    assert torch.allclose(LF.edge_length(pos, adj), want)
+    assert torch.allclose(LF.total_edge_length(p2p, adj), want)
+    # triangle areas [1.22474, 4, 3.5, 8.3666]
+    v = torch.tensor([[0, 0, 0], [1, 0, 0], [1, 1, 1], [0, 0, 2], [0, 2, 0], [0, 1, 5], [2, 2, 2], [2, 7, 0],
+                      [2, 3, 5], [2, 7, 8], [0, 3, 2]], dtype=torch.float32).cuda()
+    f = torch.tensor([[1, 2, 8], [3, 4, 5], [0, 1, 7], [6, 9, 10]]).cuda()
+    assert torch.allclose(surface_areas(v, f).cpu(), torch.tensor([1.22474, 4.0, 3.5, 8.3666]), rtol=1e-5)
+    assert sample(v, f, num_points=2000).shape == (2000, 3)
+
+
+def _load(golden):
+    g = golden("sampling_losses")
+    t = lambda k: torch.as_tensor(g[k])
+    return g, t
+
+
+def test_areas_and_sampling_match_reference(lib, golden):
+    from meshrcnn_b200 import functional as F_
+    g, t = _load(golden)
+    v_index, f_index = g["v_index"].tolist(), g["f_index"].tolist()
+    pos = cuda(g["pos"], grad=True)
+    faces = cuda(g["faces"]).long()
+    close(F_.face_areas(pos, faces, v_index, f_index), g["f64__areas"], what="areas")
+    # injected face indices + barycentric draws == the reference's sample() under the same draws
+    cloud, fidx = F_.sample_points(pos, faces, v_index, f_index, int(g["n_points"]), face_idx=cuda(g["fi_p"]).long(),
+                                   xi2=cuda(g["xi2_p"]), xi1=cuda(g["xi1_p"]))
+    close(cloud, g["f64__cloud"], what="cloud")
+    (cloud * cuda(g["f64__gcloud"])).sum().backward()
+    close(pos.grad, g["f64__cloud_gpos"], what="cloud grad")
+    # the kernel's own inverse-CDF draw from injected uniforms == oracle face_cdf_draw
+    cloud2, fidx2 = F_.sample_points(pos.detach(), faces, v_index, f_index, int(g["n_points"]), u=cuda(g["u_p"]),
+                                     xi2=cuda(g["xi2_p"]), xi1=cuda(g["xi1_p"]))
+    f_off = np.concatenate([[0], np.cumsum(f_index)])[:-1]
+    local = fidx2.cpu().numpy() - f_off[:, None]
+    mism = (local != g["fi_p"]).mean()
+    assert mism < 2e-3, mism          # fp32 areas vs fp64 oracle areas can move a draw that sits on a CDF boundary
+    if mism == 0:
+        close(cloud2, g["f64__cloud"], what="cloud (cdf draw)")
+
+
+def test_philox_sampling_distribution(lib):
+    """Own-RNG path: faces are drawn proportionally to area (chi-square), points lie on their triangles,
+    reproducible under torch.manual_seed."""
+    from meshrcnn_b200 import functional as F_
+    v = torch.tensor([[0, 0, 0], [1, 0, 0], [0, 1, 0], [3, 0, 0], [0, 3, 0], [0, 0, 0.5]], dtype=torch.float32).cuda()
+    f = torch.tensor([[0, 1, 2], [0, 3, 4], [0, 1, 5]]).cuda()
+    areas = mesh_ops.surface_areas(v.cpu().double(), f.cpu())
+    n = 200000
+    torch.manual_seed(7)
+    cloud, fidx = F_.sample_points(v, f, [6], [3], n)
+    torch.manual_seed(7)
+    cloud_b, fidx_b = F_.sample_points(v, f, [6], [3], n)
+    assert torch.equal(cloud, cloud_b) and torch.equal(fidx, fidx_b)
+    counts = torch.bincount(fidx.flatten().long().cpu(), minlength=3).double()
+    expect = areas / areas.sum() * n
+    chi2 = float(((counts - expect) ** 2 / expect).sum())
+    assert chi2 < 20.0, (chi2, counts, expect)          # 2 dof; P(chi2 > 20) ~ 5e-5
+    assert abs(float(cloud.mean())) < 1e-3              # centred
+
+
+def test_chamfer_knn_vs_oracle(lib, golden):
+    from meshrcnn_b200 import functional as F_
+    g, t = _load(golden)
+    p, q = cuda(g["f64__cloud"], grad=True), cuda(g["f64__cloud_gt"])
+    k = int(g["k"])
+    l1, l2, ip, iq, kp, kq = F_.chamfer_knn(p, q, k)
+    assert np.array_equal(ip.cpu().numpy(), g["f64__idx_p"]) and np.array_equal(iq.cpu().numpy(), g["f64__idx_gt"])
+    assert np.array_equal(kp.sort(-1).values.cpu().numpy(), g["f64__knn_p"])
+    assert np.array_equal(kq.sort(-1).values.cpu().numpy(), g["f64__knn_gt"])
+    d = mesh_ops.p2p_distance(t("f64__cloud"), t("f64__cloud_gt"))
+    w1, _, w2, _ = mesh_ops.chamfer(d)
+    close(l1, w1, what="loss_1")
+    close(l2, w2, what="loss_2")
+
+
+@pytest.mark.parametrize("B,P,Q,k", [(2, 1000, 1000, 10), (3, 777, 1301, 4), (1, 5, 2049, 0), (2, 130, 64, 16)])
+def test_knn_ragged_sizes_vs_oracle(lib, B, P, Q, k):
+    from meshrcnn_b200 import functional as F_
+    gen = torch.Generator().manual_seed(B * 1000 + P)
+    p, q = torch.rand(B, P, 3, generator=gen) - 0.5, torch.rand(B, Q, 3, generator=gen) - 0.5
+    l1, l2, ip, iq, kp, kq = F_.chamfer_knn(p.cuda(), q.cuda(), k)
+    d = mesh_ops.p2p_distance(p.double(), q.double())
+    w1, wi1, w2, wi2 = mesh_ops.chamfer(d)
+    close(l1, w1, what="l1")
+    close(l2, w2, what="l2")
+    assert torch.equal(ip.cpu().long(), wi1) and torch.equal(iq.cpu().long(), wi2)
+    if k:
+        for got, dd in ((kp, d), (kq, d.transpose(1, 2))):
+            want = dd.topk(k, dim=2, largest=False).indices.sort(-1).values
+            assert torch.equal(got.cpu().long().sort(-1).values, want)
+
+
+def test_mesh_loss_matches_reference(lib, golden):
+    """Full stage loss with injected randomness vs the unmodified reference (golden, fp64 run)."""
+    from meshrcnn_b200 import loss_functions as LF
+    g, t = _load(golden)
+    v_index, f_index = g["v_index"].tolist(), g["f_index"].tolist()
+    pos = cuda(g["pos"], grad=True)
+    faces, adj = cuda(g["faces"]).long(), cuda(g["adj"]).long()
+    batch = FakeBatch((cuda(g["gt_pos"]), cuda(g["gt_faces"]).long()), g["gt_v_index"].tolist(), g["gt_f_index"].tolist())
+    rnd = (dict(face_idx=cuda(g["fi_p"]).long(), xi2=cuda(g["xi2_p"]), xi1=cuda(g["xi1_p"])),
+           dict(face_idx=cuda(g["fi_g"]).long(), xi2=cuda(g["xi2_g"]), xi1=cuda(g["xi1_g"])))
+    ch, nl, ed = LF.mesh_loss(pos, faces, adj, v_index, f_index, batch, float(g["n_points"]), int(g["k"]), randomness=rnd)
+    close(ch, g["f64__chamfer"], what="chamfer")
+    close(ed, g["f64__edge"], what="edge")
+    gch, = torch.autograd.grad(ch, pos, retain_graph=True)
+    close(gch, g["f64__chamfer_gpos"], what="chamfer grad")
+    ged, = torch.autograd.grad(ed, pos, retain_graph=True)
+    close(ged, g["f64__edge_gpos"], what="edge grad")
+    # normal loss: against the oracle evaluated with the kernel's eigenvector sign convention
+    close(nl, g["f64__normal_canonical"], what="normal (canonical signs)")
+    gnl, = torch.autograd.grad(nl, pos)
+    want = torch.as_tensor(g["f64__normal_canonical_gpos"])
+    err = (gnl.cpu().double() - want).abs()
+    tol = 1e-4 * want.abs() + 1e-4 * float(want.abs().max())
+    frac_bad = float((err > tol).double().mean())
+    assert frac_bad < 5e-3, frac_bad      # ill-conditioned rows (near-degenerate eigen-gaps) excepted, SURVEY section 7
+    # informational distance to the raw reference value (LAPACK's own signs): same order of magnitude
+    assert abs(float(nl) - float(g["f64__normal"])) < 0.5 * abs(float(g["f64__normal"]))
+
+
+def test_normals_eigenvectors_vs_oracle(lib):
+    """compute_normals with injected k-NN sets: row 0 of the canonically signed eigenvector matrix."""
+    from meshrcnn_b200 import functional as F_
+    gen = torch.Generator().manual_seed(3)
+    B, P, k = 2, 500, 10
+    pt = torch.rand(B, P, 3, generator=gen)
+    nn = torch.stack([torch.stack([torch.randperm(P, generator=gen)[:k] for _ in range(P)]) for _ in range(B)])
+    got = F_.compute_normals(pt.cuda(), nn.cuda())
+    want = mesh_ops.normals_from_neighbours(pt.double(), nn, canonical_signs=True)
+    close(got, want, rtol=1e-5, atol=1e-5, what="normals")
+    assert torch.allclose(got.norm(dim=2).cpu(), torch.ones(B, P), atol=1e-5)
+
+
+def test_batched_mesh_loss_runs_and_is_finite(lib):
+    """Three stages, own RNG, gradient reaches the positions (shape/finite check at 10k points)."""
+    from meshrcnn_b200 import loss_functions as LF, synthetic
+    from meshrcnn_b200.layers import Cubify
+    from meshrcnn_b200.mesh_sampling import normalize_mesh
+    B = 2
+    verts, vi, faces, fi, adj = Cubify(0.2)(synthetic.blob_voxels(B, 16, 0).cuda())
+    gv, gvi, gfaces, gfi, _ = Cubify(0.5)(synthetic.blob_voxels(B, 16, 1000).cuda())
+    gt = torch.cat([normalize_mesh(v) for v in gv.split(gvi)])
+    batch = FakeBatch((gt, gfaces), gvi, gfi)
+    pos = [(verts * 0.05 + 0.01 * i).requires_grad_() for i in range(3)]
+    ch, nl, ed = LF.batched_mesh_loss(pos, faces, adj, vi, fi, batch)
+    (ch + 0.1 * nl + 0.5 * ed).backward()
+    for t in (ch, nl, ed):
+        assert t.dim() == 0 and bool(torch.isfinite(t))
+    for p in pos:
+        assert bool(torch.isfinite(p.grad).all()) and float(p.grad.abs().sum()) > 0
