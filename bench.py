@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Benchmark of the voxel-to-mesh refinement hot path (BASELINE.json metric: meshes/s, fwd+bwd, 3 refine stages).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path (one process per GPU)
+    python bench.py --impl reference [--steps K] [--warmup W]      # the reference's CPU algorithm (oracle port)
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on for one GPU): Pix3D head, random-init,
+batch 32 of synthetic 24^3 blob voxel probabilities (threshold 0.2) + 32 x 256 x 12 x 12 RoI feature maps for 224 x 224
+images, 3 x VertixRefinePix3D, chamfer / normal / edge losses on 10 000-point clouds (k = 10) against ground-truth
+meshes = normalised Cubify(0.5) of a second blob set, weighted sum, backward to the GCN weights and the feature maps.
+A "step" = Cubify + 3 stages + losses + backward over one batch.  With N GPUs every rank runs its own batch of 32
+(weak scaling) and the weight gradients are all-reduced (SUM) with NCCL inside the timed region.
+
+One JSON line on stdout (rank 0).  `value` = steps with inputs resident in HBM; `e2e` = the same through the public
+module API with inputs in pinned host memory, H2D + D2H inside the timed region.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_GPU = 32
+GRID = 24
+THRESH = 0.2
+IMG = 224
+N_POINTS = 10000
+KNN = 10
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:     # noqa: BLE001
+            self.nv = None
+            log("[bench] NVML unavailable:", e)
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:      # noqa: BLE001
+                pass
+            self._stop_evt.wait(0.05)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------------------------
+def make_inputs(B, seed):
+    """Host (CPU) tensors of one batch: voxel probabilities, feature map, GT voxel probabilities."""
+    from meshrcnn_b200 import synthetic
+    vox = synthetic.blob_voxels(B, GRID, seed)
+    fmap = synthetic.feature_maps(B, [synthetic.PIX3D_MAP], seed)[0]
+    gt_vox = synthetic.blob_voxels(B, GRID, seed + 1000)
+    return vox, fmap, gt_vox
+
+
+def algorithmic_work(stats):
+    """Algorithmic bytes / pairs per step of the kernels the roofline block reports."""
+    B, SV, SF, E = stats["B"], stats["SV"], stats["SF"], stats["E"]
+    return {
+        # k-NN / chamfer: B*P*Q point pairs per direction, 2 directions, 3 stages
+        "knn_pairs_per_launch": B * N_POINTS * N_POINTS,
+        "knn_bytes_per_launch": 12 * B * 2 * N_POINTS + (8 + 4 * KNN) * B * N_POINTS,
+        "cubify_bytes": 4 * B * GRID ** 3 + 12 * SV + 24 * SF + 16 * E + 16 * B,
+        # CSR gather (128 wide): compulsory 2 * 4 * SV * D + 4 * (E + SV + 1)
+        "gather_bytes_per_launch": 2 * 4 * SV * 128 + 4 * (E + SV + 1),
+    }
+
+
+def run_cuda(args):
+    import torch.distributed as dist
+    from meshrcnn_b200 import _lib, build
+    from meshrcnn_b200.layers import Cubify
+    from meshrcnn_b200.mesh_sampling import normalize_mesh
+    from meshrcnn_b200.pipeline import MeshTargets, RefinementHead, weighted_loss
+    from meshrcnn_b200.sharding import FlatGradBucket
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+    _lib.load()
+
+    B = B_PER_GPU
+    vox_h, fmap_h, gt_vox_h = make_inputs(B, seed=rank)          # every rank owns a different shard of meshes
+    vox_pin, fmap_pin = vox_h.pin_memory(), fmap_h.pin_memory()
+    sizes = [(IMG, IMG)] * B
+
+    torch.manual_seed(1)                                         # identical weights on every rank
+    head = RefinementHead("pix3d", cubify_threshold=THRESH).to(dev).train()
+    bucket = FlatGradBucket(head.parameters())
+
+    # ground truth: normalised Cubify(0.5) of a second blob set (the reference's own GT recipe, download_dataset.py:88-114)
+    gv, gvi, gfaces, gfi, _ = Cubify(0.5)(gt_vox_h.to(dev))
+    gt = MeshTargets(torch.cat([normalize_mesh(v) for v in gv.split(gvi)]), gfaces, gvi, gfi)
+
+    def step(vox_d, fmap_d):
+        bucket.zero()
+        fmap_d.grad = None
+        losses = head(vox_d, fmap_d, sizes, gt)
+        weighted_loss(losses).backward()
+        bucket.all_reduce()
+        return losses
+
+    vox_d = vox_h.to(dev)
+    fmap_d = fmap_h.to(dev).requires_grad_()
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up -------------------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        losses = step(vox_d, fmap_d)
+    sync_all()
+    verts, vi, faces, fi, adj = head.cubify(vox_d)
+    stats = {"B": B, "SV": int(verts.shape[0]), "SF": int(faces.shape[0]), "E": int(adj.shape[1])}
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    # ---- timed region 1: inputs resident in HBM ----------------------------------------------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sync_all()
+    l0 = _lib.launch_count
+    for a, b in ev:
+        flush.zero_()                      # L2 flush between timed iterations (outside the event bracket)
+        a.record()
+        step(vox_d, fmap_d)
+        b.record()
+    sync_all()
+    launches = (_lib.launch_count - l0) // args.steps
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    # ---- timed region 2: end to end through the module API from pinned host memory --------------------------------
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    host_losses = None
+    sync_all()
+    for a, b in ev2:
+        flush.zero_()
+        a.record()
+        v = vox_pin.to(dev, non_blocking=True)
+        f = fmap_pin.to(dev, non_blocking=True).requires_grad_()
+        losses = step(v, f)
+        host_losses = torch.stack([losses["chamfer_loss"], losses["normal_loss"], losses["edge_loss"]]).cpu()   # D2H
+        b.record()
+    sync_all()
+    e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
+    clocks = sampler.stop() if sampler else None
+
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)                  # max over ranks
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    # ---- per-kernel breakdown (instrumented extra steps, not part of the headline numbers) -------------------------
+    breakdown, roofline, roof_all = None, None, None
+    if rank == 0:
+        with _lib.timed_calls() as tc:
+            for _ in range(2):
+                step(vox_d, fmap_d)
+        breakdown = {k: {"ms_per_step": round(v / 2, 4), "calls_per_step": tc.calls[k] // 2} for k, v in
+                     sorted(tc.ms.items(), key=lambda kv: -kv[1])}
+        peaks = {"hbm_gbs": 6650.0, "src": "fallback"}
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            peaks = json.load(open(pk))
+            peaks["src"] = "measured"
+        work = algorithmic_work(stats)
+        top = next(iter(breakdown))
+        roof_all = {}
+        if "mrb_knn_fwd" in breakdown:
+            per = breakdown["mrb_knn_fwd"]["ms_per_step"] / breakdown["mrb_knn_fwd"]["calls_per_step"] * 1e-3
+            fp32_peak = 148 * 128 * 1.965e9 / 1e12            # T lane-FMA/s at max clock (no measured figure available)
+            roof_all["mrb_knn_fwd"] = {"bound": "fp32-issue", "achieved": round(work["knn_pairs_per_launch"] / per / 1e12, 3),
+                                       "peak": round(fp32_peak / 9.0, 3), "unit": "Tpairs/s (peak = FP32 issue rate / 9 instr per pair)",
+                                       "hbm_gbs": round(work["knn_bytes_per_launch"] / per / 1e9, 2)}
+        if "mrb_csr_gather_fwd" in breakdown:
+            per = breakdown["mrb_csr_gather_fwd"]["ms_per_step"] / breakdown["mrb_csr_gather_fwd"]["calls_per_step"] * 1e-3
+            a = work["gather_bytes_per_launch"] / per / 1e9
+            roof_all["mrb_csr_gather_fwd"] = {"bound": "hbm", "achieved": round(a, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                              "frac": round(a / peaks["hbm_gbs"], 4)}
+        if "mrb_cubify_emit" in breakdown:
+            per = (breakdown["mrb_cubify_emit"]["ms_per_step"] + breakdown["mrb_cubify_count"]["ms_per_step"]) * 1e-3
+            a = work["cubify_bytes"] / per / 1e9
+            roof_all["mrb_cubify"] = {"bound": "hbm", "achieved": round(a, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                      "frac": round(a / peaks["hbm_gbs"], 4)}
+        # the JSON contract's `roofline` block: the dominant kernel of the step
+        if top == "mrb_knn_fwd":
+            per = breakdown[top]["ms_per_step"] / breakdown[top]["calls_per_step"] * 1e-3
+            a = work["knn_bytes_per_launch"] / per / 1e9
+            roofline = {"kernel": "k_nn<10> (mrb_knn_fwd)", "bound": "hbm", "achieved": round(a, 2), "peak": peaks["hbm_gbs"],
+                        "unit": "GB/s", "frac": round(a / peaks["hbm_gbs"], 5), "traffic": None, "peak_src": peaks["src"],
+                        "note": "dominant kernel is FP32-issue bound, not HBM/tensor bound (SURVEY 8d): see roofline_kernels"}
+        else:
+            r = roof_all.get(top) or next(iter(roof_all.values()))
+            roofline = dict(r, kernel=top, traffic=None, peak_src=peaks["src"])
+
+    result = None
+    if rank == 0:
+        total_meshes = B * world * args.steps
+        result = {
+            "metric": "meshes/sec (fwd+bwd, 3 refine stages)", "value": round(total_meshes / (dev_ms * 1e-3), 2),
+            "unit": "meshes/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(dev_ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "pix3d head: batch %d/GPU, %d^3 blob voxels th=%.1f, 256x12x12 RoI features, %dpx images, "
+                                   "3 x VertixRefinePix3D, 10k-point chamfer+normal(k=10)+edge losses, fwd+bwd (BASELINE configs[1])"
+                                   % (B, GRID, THRESH, IMG),
+                       "global_batch": B * world, "parallelism": "mesh-sharded dp%d, NCCL grad all-reduce(SUM)" % world,
+                       "per_gpu": stats, "l2": "256 MiB flush write between timed iterations",
+                       "optimizer": "none (metric is fwd+bwd)"},
+            "e2e": {"value": round(total_meshes / (e2e_ms * 1e-3), 2), "unit": "meshes/s",
+                    "h2d_bytes_per_step": int(vox_pin.numel() * 4 + fmap_pin.numel() * 4), "d2h_bytes_per_step": 12,
+                    "ms_per_step": round(e2e_ms / args.steps, 3)},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_kernels": roof_all,
+            "breakdown_ms": breakdown,
+            "losses": {k: float(v) for k, v in zip(("chamfer", "normal", "edge"), host_losses)},
+        }
+        if args.cpu_baseline:
+            result["cpu_baseline"] = cpu_reference(steps=1, warmup=0, meshes=2)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if result is not None:
+        print(json.dumps(result), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU algorithm (oracle port) on the host cores
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_reference(steps, warmup, meshes):
+    """Times the oracle restatement of the reference path (numpy Cubify + torch-CPU stages and losses with dense
+    distance matrices, topk, LAPACK eigh, autograd backward) on `meshes` meshes of the bench workload."""
+    from oracle import cubify_np, mesh_ops
+    from meshrcnn_b200 import synthetic
+    from meshrcnn_b200.layers import VertixRefinePix3D
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    vox, fmap, gt_vox = make_inputs(meshes, seed=0)
+    torch.manual_seed(1)
+    stages = [VertixRefinePix3D(use_input_features=bool(i)) for i in range(3)]
+    params = [{k: v.detach().clone().requires_grad_() for k, v in st.named_parameters()} for st in stages]
+    sizes = [(IMG, IMG)] * meshes
+    gv, gvi, gf, gfi, _ = cubify_np.cubify(gt_vox.numpy(), 0.5)
+    gt_pos = torch.cat([mesh_ops.normalize_cloud(v) for v in torch.from_numpy(gv).split(gvi)])
+    gt_faces = torch.from_numpy(gf)
+
+    def one_step():
+        verts, vi, faces, fi, adj = cubify_np.cubify(vox.numpy(), THRESH)
+        pos, faces, adj = torch.from_numpy(verts), torch.from_numpy(faces), torch.from_numpy(adj)
+        fm = fmap.clone().requires_grad_()
+        feats, cur, positions = None, pos, []
+        for sd in params:
+            cur, feats = mesh_ops.stage_pix3d(sd, vi, fm, adj, cur, sizes, feats=feats)
+            positions.append(cur)
+        total = 0
+        for s, p in enumerate(positions):
+            u, x2, x1 = synthetic.sampling_randomness(meshes, N_POINTS, 10 + s)
+            ug, x2g, x1g = synthetic.sampling_randomness(meshes, N_POINTS, 20 + s)
+            fi_p = torch.stack([mesh_ops.face_cdf_draw(v.detach(), f, u[b]) for b, (v, f) in
+                                enumerate(zip(p.split(vi), faces.split(fi)))])
+            fi_g = torch.stack([mesh_ops.face_cdf_draw(v, f, ug[b]) for b, (v, f) in
+                                enumerate(zip(gt_pos.split(gvi), gt_faces.split(gfi)))])
+            ch, nl, ed, _ = mesh_ops.mesh_loss_with(p, faces, adj, vi, fi, gt_pos, gt_faces, gvi, gfi, (fi_p, x2, x1),
+                                                    (fi_g, x2g, x1g), float(N_POINTS), KNN)
+            total = total + ch + 0.1 * nl + 0.5 * ed
+        total.backward()
+        return float(total)
+
+    for _ in range(warmup):
+        one_step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        one_step()
+        times.append(time.perf_counter() - t0)
+    sec = sum(times)
+    return {"value": round(meshes * steps / sec, 4), "unit": "meshes/s", "cores": cores, "kind": "port",
+            "sample": "%d step(s) of %d meshes of the bench workload (same grids, maps, weights, 10k-point clouds, k=10), "
+                      "oracle port of the reference CPU algorithm, torch threads=%d" % (steps, meshes, torch.get_num_threads()),
+            "s_per_step": round(sec / steps, 3)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return                       # rank 0 alone runs the CPU arm
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    meshes = 2 if (args.steps + args.warmup) <= 6 else 1
+    cb = cpu_reference(steps=args.steps, warmup=args.warmup, meshes=meshes)
+    line = {
+        "impl": "reference", "metric": "meshes/sec (fwd+bwd, 3 refine stages)", "value": cb["value"], "unit": "meshes/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(cb["s_per_step"] * 1e3, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "pix3d head (BASELINE configs[1]) -- CPU arm: bounded sample of %d mesh(es) per step" % meshes},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "meshes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            args.cpu_baseline = args.cpu_baseline and int(os.environ.get("WORLD_SIZE", "1")) == 1
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,94 @@
+"""The refinement-stage loop: Cubify -> stage 0 (no input features) -> stages 1.. (with features)
+-> training losses or the eval output dict.  Mirrors the hot-path section of ``ShapeNetModel.forward``
+(reference meshRCNN/shapenet_model.py:71-99) and ``Pix3DModel.forward`` (meshRCNN/pix3d_model.py:87-115); the
+backbone / voxel branch upstream of it are out of scope and are replaced by the ``voxel_probs`` /
+``feature_maps`` arguments.
+"""
+from typing import List, Optional, Sequence, Tuple, Union
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from .layers import Cubify, ResVertixRefineShapenet, VertixRefinePix3D, VertixRefineShapeNet
+from .loss_functions import batched_mesh_loss
+
+
+class MeshTargets:
+    """Ground-truth side of a packed batch; same fields as reference ``data.dataloader.Batch`` (:21-36) that the
+    losses read: ``meshes = (vertices SVgt x 3, faces SFgt x 3 local ids)``, ``vertice_index``, ``face_index``."""
+
+    def __init__(self, vertices: Tensor, faces: Tensor, vertice_index: Sequence[int], face_index: Sequence[int]):
+        self.meshes = (vertices, faces)
+        self.vertice_index = list(vertice_index)
+        self.face_index = list(face_index)
+
+    def to(self, *args, **kwargs):
+        v, f = self.meshes
+        return MeshTargets(v.to(*args, **kwargs), f.to(*args, **kwargs), self.vertice_index, self.face_index)
+
+    def slice(self, lo: int, hi: int) -> "MeshTargets":
+        v, f = self.meshes
+        vo, fo = sum(self.vertice_index[:lo]), sum(self.face_index[:lo])
+        vn, fn = sum(self.vertice_index[lo:hi]), sum(self.face_index[lo:hi])
+        return MeshTargets(v[vo:vo + vn], f[fo:fo + fn], self.vertice_index[lo:hi], self.face_index[lo:hi])
+
+
+class RefinementHead(nn.Module):
+    """``cubify`` + ``refineStages`` with the reference's attribute names (state-dict keys ``cubify.*``,
+    ``refineStages.{i}.*`` as in shapenet_model.py:27-41 / pix3d_model.py:32-44).
+
+    ``model``: "pix3d" (VertixRefinePix3D, 256-channel RoI map), "shapenet" (VertixRefineShapeNet) or
+    "shapenet_residual" (ResVertixRefineShapenet)."""
+
+    def __init__(self, model: str = "pix3d", cubify_threshold: float = 0.2, alignment_channels: Optional[int] = None,
+                 vertex_feature_dim: int = 128, num_refinement_stages: int = 3):
+        super().__init__()
+        cls = {"pix3d": VertixRefinePix3D, "shapenet": VertixRefineShapeNet,
+               "shapenet_residual": ResVertixRefineShapenet}[model]
+        if alignment_channels is None:
+            alignment_channels = 256 if model == "pix3d" else 3840
+        self.model = model
+        self.cubify = Cubify(cubify_threshold)
+        stages = [cls(alignment_size=alignment_channels, use_input_features=False, num_features=vertex_feature_dim)]
+        for _ in range(num_refinement_stages - 1):
+            stages.append(cls(alignment_size=alignment_channels, use_input_features=True,
+                              num_features=vertex_feature_dim))
+        self.refineStages = nn.ModuleList(stages)
+
+    def forward(self, voxel_probs: Tensor, feature_maps: Union[Tensor, List[Tensor]], image_sizes,
+                targets: Optional[MeshTargets] = None, mesh_index: Optional[List[int]] = None,
+                loss_randomness=None) -> dict:
+        if self.training and targets is None:
+            raise ValueError("In training mode, targets should be passed")
+        mesh_index = [1 for _ in image_sizes] if mesh_index is None else mesh_index
+        pos0, vertice_index, faces, face_index, adj_index = self.cubify(voxel_probs)
+        pos1, feats = self.refineStages[0](vertice_index, feature_maps, adj_index, pos0, image_sizes,
+                                           mesh_index=mesh_index)
+        positions = [pos0, pos1]
+        for stage in self.refineStages[1:]:
+            new_pos, feats = stage(vertice_index, feature_maps, adj_index, positions[-1], image_sizes,
+                                   mesh_index=mesh_index, vertex_features=feats)
+            positions.append(new_pos)
+        out = {}
+        if self.training:
+            chamfer, normal, edge = batched_mesh_loss(positions[1:], faces, adj_index, vertice_index, face_index, targets,
+                                                      randomness=loss_randomness)
+            out.update({"chamfer_loss": chamfer, "edge_loss": edge, "normal_loss": normal})
+        else:
+            out.update({"vertex_positions": positions, "edge_index": adj_index, "face_index": face_index,
+                        "vertice_index": vertice_index, "faces": faces, "mesh_index": mesh_index})
+        return out
+
+
+# default loss weights of the reference CLI (train.py:19-74): chamfer 1, normal 0.1, edge 0.5
+LOSS_WEIGHTS = {"chamfer_loss": 1.0, "normal_loss": 0.1, "edge_loss": 0.5}
+
+
+def weighted_loss(losses: dict, weights: dict = LOSS_WEIGHTS) -> Tensor:
+    """Weighted sum of the loss dict (reference utils/train_utils.py:208-225)."""
+    total = None
+    for k, w in weights.items():
+        if k in losses:
+            total = losses[k] * w if total is None else total + losses[k] * w
+    return total

@@ -1,0 +1,71 @@
+"""Multi-GPU: one process per GPU, meshes sharded by index, one NCCL all-reduce(SUM) of the gradients.
+
+Replaces the reference's single-process ``dataParallel.CustomDP`` (dataParallel/dataParallel.py:28-46): per-forward
+parameter broadcast (replicate.py:26-43), Python-thread ``parallel_apply`` and ``reduce_add`` of the losses
+(gather.py:13-28,109-112).  Here weights stay resident on every rank, every rank runs the hot path on its own packed
+shard (meshes are independent units -- adjacency is block-diagonal per mesh), and the only exchange step is the
+gradient all-reduce -- SUM, not mean, like the reference's reduce-add -- over NVLink/NVSwitch.
+"""
+from typing import Iterable, List, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+
+def split_to_n(n_items: int, n_parts: int) -> List[Tuple[int, int]]:
+    """Contiguous [lo, hi) chunks; the first ``n_items % n_parts`` chunks get one extra item -- the reference's
+    ``split_to_n`` (dataParallel/scatter.py:5-13), kept so that results match the reference DP shard for shard."""
+    base, extra = divmod(n_items, n_parts)
+    out, lo = [], 0
+    for r in range(n_parts):
+        hi = lo + base + (1 if r < extra else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
+def balanced_split(costs: List[float], n_parts: int) -> List[List[int]]:
+    """Greedy longest-processing-time assignment of meshes to ranks by a per-mesh cost (e.g. occupied-voxel count);
+    optional throughput mode (mesh sizes vary ~1.4x), not used for parity runs."""
+    order = sorted(range(len(costs)), key=lambda i: -costs[i])
+    loads = [0.0] * n_parts
+    parts: List[List[int]] = [[] for _ in range(n_parts)]
+    for i in order:
+        r = min(range(n_parts), key=lambda j: loads[j])
+        parts[r].append(i)
+        loads[r] += costs[i]
+    return [sorted(p) for p in parts]
+
+
+class FlatGradBucket:
+    """All parameter gradients live in one contiguous fp32 buffer (``p.grad`` are views into it), so the step's
+    exchange is a single all-reduce launch: 1.9 MB for the Pix3D head, 8.9 MB for the residual ShapeNet head."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self) -> None:
+        self.flat.zero_()
+
+    def all_reduce(self, async_op: bool = False):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
+        return None
+
+
+def all_reduce_losses(losses: dict) -> dict:
+    """Replica losses are summed (reference gather.py:109-112)."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return losses
+    keys = sorted(losses)
+    buf = torch.stack([losses[k].detach().float() for k in keys])
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    return {k: buf[i] for i, k in enumerate(keys)}
