@@ -1,0 +1,138 @@
+"""CPU: host-side logic (sharding, synthetic generators, module / state-dict surface) and the world_size-2 gloo path."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_split_to_n_matches_reference_semantics():
+    from meshrcnn_b200.sharding import balanced_split, split_to_n
+    assert split_to_n(10, 4) == [(0, 3), (3, 6), (6, 8), (8, 10)]      # first len % n chunks get one extra
+    assert split_to_n(256, 8) == [(32 * r, 32 * r + 32) for r in range(8)]
+    assert split_to_n(3, 4) == [(0, 1), (1, 2), (2, 3), (3, 3)]
+    parts = balanced_split([5, 3, 8, 1, 2, 7], 2)
+    assert sorted(sum(parts, [])) == list(range(6))
+    loads = [sum([5, 3, 8, 1, 2, 7][i] for i in p) for p in parts]
+    assert abs(loads[0] - loads[1]) <= 2
+
+
+def test_synthetic_inputs_are_deterministic_and_sized():
+    from meshrcnn_b200 import synthetic
+    a, b = synthetic.blob_voxels(4, 32, 0), synthetic.blob_voxels(4, 32, 0)
+    assert torch.equal(a, b) and a.shape == (4, 32, 32, 32)
+    occ = float((a > 0.2).float().mean())
+    assert 0.12 < occ < 0.25                                            # ~18.5 %
+    pos = synthetic.in_frustum_positions(1000, 224, 0)
+    h = 248 * (pos[:, 1] / pos[:, 2]) + 111.5
+    w = 248 * (pos[:, 0] / -pos[:, 2]) + 111.5
+    assert bool(((h > 0) & (h < 223) & (w > 0) & (w < 223)).all())
+
+
+def test_module_surface_and_state_dict_keys():
+    """Names, constructor arguments and state-dict keys of reference meshRCNN/layers.py."""
+    import inspect
+    import meshrcnn_b200.layers as L
+    from meshrcnn_b200.pipeline import RefinementHead
+    head = RefinementHead("shapenet_residual")
+    keys = set(head.state_dict())
+    assert {"cubify.kernel", "cubify.deltas", "refineStages.0.linear.weight", "refineStages.0.resGraphConv0.conv0.w0",
+            "refineStages.0.resGraphConv0.projection.weight", "refineStages.2.graphConv.w1"} <= keys
+    assert head.cubify.kernel.shape == (6, 1, 3, 3, 3) and head.cubify.deltas.shape == (6, 4, 5)
+    assert head.refineStages[0].resGraphConv0.conv0.w0.shape == (131, 128)      # stored in x out
+    assert head.refineStages[1].resGraphConv0.conv0.w0.shape == (259, 128)
+    assert sum(p.numel() for p in head.parameters()) == 2217600
+    assert sum(p.numel() for p in RefinementHead("pix3d").parameters()) == 466843
+    sig = inspect.signature(L.ResVertixRefineShapenet.forward)
+    assert list(sig.parameters)[1:] == ["vertice_index", "img_feature_maps", "vertex_adjacency", "vertex_positions",
+                                        "image_sizes", "vertex_features", "mesh_index"]
+    sig = inspect.signature(L.VertixRefinePix3D.forward)
+    assert list(sig.parameters)[1:] == ["vertice_index", "back_bone_features", "vertex_adjacency", "vertex_positions",
+                                        "image_sizes", "mesh_index", "vertex_features"]
+    k = L.Cubify(0.5).kernel
+    assert k[2, 0, 1, 1, 1] == 1 and k[2, 0, 1, 2, 1] == -1 and float(k[2].sum()) == 0
+    d = L.Cubify(0.5).deltas
+    assert d[2, 0].tolist() == [0, 0, 0.5, -0.5, -0.5] and d[4, 1].tolist() == [0, 0, -0.5, -0.5, -0.5]
+
+
+def test_sharded_losses_recombine_like_reference_dp():
+    """Chamfer / normal terms are batch sums, so per-shard values add up to the unsharded value; the edge loss is a
+    per-replica mean that the reference DP sums over replicas (gather.py:109-112) -- SURVEY 8e."""
+    from oracle import cubify_np, mesh_ops
+    from meshrcnn_b200 import synthetic
+    from meshrcnn_b200.sharding import split_to_n
+    B, n, k = 4, 200, 4
+    verts, vi, faces, fi, adj = cubify_np.cubify(synthetic.blob_voxels(B, 8, 0).numpy(), 0.2)
+    gverts, gvi, gfaces, gfi, _ = cubify_np.cubify(synthetic.blob_voxels(B, 8, 1000).numpy(), 0.5)
+    pos = torch.from_numpy(verts).double() * 0.1
+    gpos = torch.from_numpy(gverts).double() * 0.1
+    faces, gfaces, adj = torch.from_numpy(faces), torch.from_numpy(gfaces), torch.from_numpy(adj)
+    u, x2, x1 = synthetic.sampling_randomness(B, n, 1)
+    fi_p = torch.stack([mesh_ops.face_cdf_draw(v, f, u[b]) for b, (v, f) in enumerate(zip(pos.split(vi), faces.split(fi)))])
+    fi_g = torch.stack([mesh_ops.face_cdf_draw(v, f, u[b]) for b, (v, f) in enumerate(zip(gpos.split(gvi), gfaces.split(gfi)))])
+    full = mesh_ops.mesh_loss_with(pos, faces, adj, vi, fi, gpos, gfaces, gvi, gfi, (fi_p, x2.double(), x1.double()),
+                                   (fi_g, x2.double(), x1.double()), float(n), k)
+    ch = nl = 0.0
+    edges = []
+    for lo, hi in split_to_n(B, 2):
+        vo, fo, gvo, gfo = sum(vi[:lo]), sum(fi[:lo]), sum(gvi[:lo]), sum(gfi[:lo])
+        vn, fn, gvn, gfn = sum(vi[lo:hi]), sum(fi[lo:hi]), sum(gvi[lo:hi]), sum(gfi[lo:hi])
+        sel = (adj[0] >= vo) & (adj[0] < vo + vn)
+        part = mesh_ops.mesh_loss_with(pos[vo:vo + vn], faces[fo:fo + fn], adj[:, sel] - vo, vi[lo:hi], fi[lo:hi],
+                                       gpos[gvo:gvo + gvn], gfaces[gfo:gfo + gfn], gvi[lo:hi], gfi[lo:hi],
+                                       (fi_p[lo:hi], x2[lo:hi].double(), x1[lo:hi].double()),
+                                       (fi_g[lo:hi], x2[lo:hi].double(), x1[lo:hi].double()), float(n), k)
+        ch, nl = ch + part[0], nl + part[1]
+        edges.append((part[2], int(sel.sum())))
+    assert torch.allclose(ch, full[0], rtol=1e-12) and torch.allclose(nl, full[1], rtol=1e-9)
+    recombined = sum(e * m for e, m in edges) / sum(m for _, m in edges)
+    assert torch.allclose(recombined, full[2], rtol=1e-12)
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from meshrcnn_b200.sharding import FlatGradBucket, all_reduce_losses, split_to_n
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+torch.manual_seed(0)
+lin = torch.nn.Sequential(torch.nn.Linear(5, 4, bias=False), torch.nn.Linear(4, 2, bias=False))
+bucket = FlatGradBucket(lin.parameters())
+data = torch.arange(40.).reshape(8, 5) / 10
+lo, hi = split_to_n(8, world)[rank]
+bucket.zero()
+lin(data[lo:hi]).pow(2).sum().backward()
+assert lin[0].weight.grad.data_ptr() == bucket.flat.data_ptr()          # grads accumulate straight into the bucket
+bucket.all_reduce()
+ref = torch.nn.Sequential(torch.nn.Linear(5, 4, bias=False), torch.nn.Linear(4, 2, bias=False))
+ref.load_state_dict(lin.state_dict())
+ref(data).pow(2).sum().backward()                                       # SUM over shards == unsharded gradient
+for p, q in zip(lin.parameters(), ref.parameters()):
+    assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-6), (rank, p.grad, q.grad)
+tot = all_reduce_losses({"chamfer_loss": torch.tensor(float(rank + 1)), "edge_loss": torch.tensor(2.0)})
+assert float(tot["chamfer_loss"]) == sum(range(1, world + 1)) and float(tot["edge_loss"]) == 2.0 * world
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_world_size_2_gloo_gradient_allreduce(tmp_path):
+    script = tmp_path / "gloo_worker.py"
+    script.write_text(_GLOO_WORKER % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                       capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("ok") == 2
+
+
+def test_bench_reference_arm_extra_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                       capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
