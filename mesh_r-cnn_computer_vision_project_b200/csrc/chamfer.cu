@@ -5,7 +5,7 @@
 // (reference meshRCNN/loss_functions.py:93-102,141,192-220), which materialise four dense B x P x Q fp32 tensors
 // (1.6 GB per sample at P = Q = 10k).  Here nothing is materialised: every query point streams the other cloud
 // through shared memory and keeps its running minimum / sorted top-k list in registers.  This kernel is bound
-// by the FP32 CUDA-core issue rate (B*P*Q pairs, ~9 instructions each), not by HBM or the tensor pipe: inputs
+// by the FP32 CUDA-core issue rate (B*P*Q pairs, ~5.5 instructions each), not by HBM or the tensor pipe: inputs
 // are 12 B/point and outputs <= 48 B/point.
 //
 // Distances are the direct sum of squared differences, which is *more* accurate than the reference's
@@ -17,87 +17,273 @@
 namespace mrb {
 namespace chamfer {
 
-constexpr int TILE = 1024;      // candidate points staged per shared-memory tile
-constexpr int THREADS = 128;    // one query point per thread
+constexpr int TILE = 512;       // candidate points staged per shared-memory tile
+constexpr int THREADS = 128;    // threads per CTA
+constexpr int QPT = 2;          // query points per thread (one LDS.128 of a candidate feeds both)
+constexpr int QCAP = 16;        // deferred-hit queue entries per query
+constexpr int STEP = 4;         // candidates between two warp-wide queue checks
+constexpr int SORT_MAX = 16384; // clouds up to this size are x-sorted in shared memory (pruned scan)
 
+// ---------------------------------------------------------------------------------------------------------
+// stage 0: per-cloud sort by the x coordinate (bitonic, one CTA per cloud) -> float4 (x, y, z, original index)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sortable(float x) {
+    const uint32_t u = __float_as_uint(x);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(1024) k_sort_x(const float* __restrict__ pts, int P, int N2, float4* __restrict__ out) {
+    extern __shared__ unsigned char smem_raw[];
+    uint32_t* key = reinterpret_cast<uint32_t*>(smem_raw);
+    unsigned short* idx = reinterpret_cast<unsigned short*>(key + N2);
+    const float* src = pts + (size_t)blockIdx.x * P * 3;
+    for (int i = threadIdx.x; i < N2; i += blockDim.x) {
+        key[i] = (i < P) ? sortable(src[3 * (size_t)i]) : 0xffffffffu;
+        idx[i] = (unsigned short)i;
+    }
+    __syncthreads();
+    for (int k = 2; k <= N2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (N2 >> 1); t += blockDim.x) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // lower index of the pair (bit j clear)
+                const int l = i | j;
+                const bool up = (i & k) == 0;
+                const uint32_t ka = key[i], kb = key[l];
+                const unsigned short ia = idx[i], ib = idx[l];
+                const bool gt = ka > kb || (ka == kb && ia > ib);       // (key, original index): total, deterministic order
+                if (gt == up) { key[i] = kb; key[l] = ka; idx[i] = ib; idx[l] = ia; }
+            }
+            __syncthreads();
+        }
+    }
+    float4* dst = out + (size_t)blockIdx.x * P;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const int o = idx[i];
+        dst[i] = make_float4(src[3 * (size_t)o], src[3 * (size_t)o + 1], src[3 * (size_t)o + 2], __int_as_float(o));
+    }
+}
+
+// clouds too large for the shared-memory sort: pack in the original order (no pruning)
+__global__ void k_pack(const float* __restrict__ pts, long long n_total, int P, float4* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_total) return;
+    out[i] = make_float4(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], __int_as_float((int)(i % P)));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// stage 1: pruned, filtered brute-force scan
+// ---------------------------------------------------------------------------------------------------------
 template <int K>
 struct TopK {
     float d[K];
     int i[K];
     __device__ __forceinline__ void init() {
 #pragma unroll
-        for (int s = 0; s < K; ++s) { d[s] = FLT_MAX; i[s] = 0; }
+        for (int s = 0; s < K; ++s) { d[s] = FLT_MAX; i[s] = 0x7fffffff; }
     }
-    // sorted ascending; ties keep the earlier (lower) candidate index first
+    // (distance, index) lexicographic order: sorted ascending, ties -> lower original index first
+    static __device__ __forceinline__ bool after(float da, int ia, float db, int ib) {
+        return da > db || (da == db && ia > ib);
+    }
+    __device__ __forceinline__ bool admits(float nd, int ni) const { return after(d[K - 1], i[K - 1], nd, ni); }
     __device__ __forceinline__ void insert(float nd, int ni) {
 #pragma unroll
         for (int s = K - 1; s > 0; --s) {
-            const bool shift = d[s - 1] > nd;
-            const bool here = d[s] > nd;
+            const bool shift = after(d[s - 1], i[s - 1], nd, ni);
+            const bool here = after(d[s], i[s], nd, ni);
             const float td = shift ? d[s - 1] : (here ? nd : d[s]);
             const int ti = shift ? i[s - 1] : (here ? ni : i[s]);
             d[s] = td; i[s] = ti;
         }
-        if (d[0] > nd) { d[0] = nd; i[0] = ni; }
+        if (after(d[0], i[0], nd, ni)) { d[0] = nd; i[0] = ni; }
     }
 };
 
-// grid: (ceil(P / THREADS), B).  For every point of `a` (B x P x 3): nearest point of `b` (B x Q x 3) -> min_d, min_i,
-// and (K > 0) the k nearest indices, sorted by distance, into knn[B][P][k_out].
+// One query point: exact top-K list plus the filter threshold derived from it.
 template <int K>
-__global__ void __launch_bounds__(THREADS) k_nn(const float* __restrict__ a, const float* __restrict__ b, int P, int Q,
-                                                float* __restrict__ min_d, int32_t* __restrict__ min_i,
+struct Query {
+    float x, y, z, pp;     // coordinates and |p|^2
+    float thr;             // filter threshold on s = |q|^2 - 2 p.q  (== d - |p|^2 up to rounding)
+    int cnt;               // queued hits of the current tile
+    TopK<K> top;
+    __device__ __forceinline__ void set_threshold(float margin) { thr = top.d[K - 1] - pp + margin; }
+    // exact re-evaluation of the queued candidates with the direct (p - q)^2 form
+    __device__ __forceinline__ void drain(const float4* __restrict__ tile, const int* __restrict__ tile_idx,
+                                          const unsigned short* __restrict__ queue, float margin) {
+        for (int j = 0; j < cnt; ++j) {
+            const int t = queue[j * THREADS];
+            const float4 c = tile[t];
+            // c = (-2qx, -2qy, -2qz, |q|^2): the coordinates are recovered exactly (power-of-two scaling)
+            const float dx = x + 0.5f * c.x, dy = y + 0.5f * c.y, dz = z + 0.5f * c.z;
+            const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            const int ci = tile_idx[t];
+            if (top.admits(d, ci)) top.insert(d, ci);
+        }
+        cnt = 0;
+        set_threshold(margin);
+    }
+};
+
+// grid: (ceil(P / (THREADS*QPT)), B).  `a` / `b` are the packed (x-sorted when prune != 0) clouds of stage 0.
+// For every point of a: squared distance + original index of the nearest point of b, and the K nearest indices sorted
+// by (distance, index); results are written at the query's original index.
+//
+// * Hot loop per candidate and query: 3 FFMA (expanded form |q|^2 - 2 p.q against a per-query threshold) + 1 compare --
+//   a conservative *filter* whose rounding error is covered by `margin`; hits are queued (2 bytes) and re-evaluated
+//   exactly when a queue fills (warp-wide) or the tile ends, so results equal an exact scan while the divergent
+//   sorted-list insertion stays out of the inner loop.
+// * Pruning: both clouds are sorted by x, a CTA's queries span a narrow x range, candidate tiles are visited outwards
+//   from that range, and a direction is abandoned once the tile's x gap alone exceeds every query's current k-th best
+//   distance.  The scan stays exact (the bound is a true lower bound of the distance).
+template <int K>
+__global__ void __launch_bounds__(THREADS) k_nn(const float4* __restrict__ a, const float4* __restrict__ b, int P, int Q,
+                                                int prune, float* __restrict__ min_d, int32_t* __restrict__ min_i,
                                                 int32_t* __restrict__ knn, int k_out) {
-    __shared__ float4 tile[TILE];
+    __shared__ float4 tile[TILE + STEP];
+    __shared__ int tile_idx[TILE];
+    __shared__ unsigned short queue[QPT][QCAP * THREADS];
+    __shared__ int qq_max_bits;
+    __shared__ float red[THREADS / 32][3];
+    __shared__ float blk[3];    // x range of the CTA's queries, max k-th best distance
     const int batch = blockIdx.y;
-    const int p = blockIdx.x * THREADS + threadIdx.x;
-    const bool active = p < P;
-    const float* ap = a + ((size_t)batch * P + (active ? p : 0)) * 3;
-    const float px = ap[0], py = ap[1], pz = ap[2];
-    const float* bq = b + (size_t)batch * Q * 3;
+    const int tid = threadIdx.x;
+    const float4* bq = b + (size_t)batch * Q;
 
-    float best = FLT_MAX;
-    int besti = 0;
-    TopK<(K > 0 ? K : 1)> top;
-    if (K > 0) top.init();
+    Query<K> qr[QPT];
+    int pidx[QPT], orig[QPT];
+    float xlo = FLT_MAX, xhi = -FLT_MAX;
+#pragma unroll
+    for (int u = 0; u < QPT; ++u) {
+        pidx[u] = (blockIdx.x * QPT + u) * THREADS + tid;
+        const float4 ap = a[(size_t)batch * P + min(pidx[u], P - 1)];   // out-of-range slots duplicate the last query
+        qr[u].x = ap.x; qr[u].y = ap.y; qr[u].z = ap.z;
+        orig[u] = __float_as_int(ap.w);
+        qr[u].pp = fmaf(ap.z, ap.z, fmaf(ap.y, ap.y, ap.x * ap.x));
+        qr[u].cnt = 0;
+        qr[u].top.init();
+        xlo = fminf(xlo, ap.x); xhi = fmaxf(xhi, ap.x);
+    }
+    // CTA-wide x range of the queries
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        xlo = fminf(xlo, __shfl_xor_sync(0xffffffffu, xlo, o));
+        xhi = fmaxf(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
+    }
+    if (lane_id() == 0) { red[warp_id()][0] = xlo; red[warp_id()][1] = xhi; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < THREADS / 32; ++w) { xlo = fminf(xlo, red[w][0]); xhi = fmaxf(xhi, red[w][1]); }
+        blk[0] = xlo; blk[1] = xhi; blk[2] = FLT_MAX;
+    }
+    __syncthreads();
+    xlo = blk[0]; xhi = blk[1];
 
-    for (int q0 = 0; q0 < Q; q0 += TILE) {
+    const int ntiles = (Q + TILE - 1) / TILE;
+    // first tile: the one holding the first candidate with x >= xlo (binary search over the sorted cloud)
+    int start = 0;
+    if (prune) {
+        int lo = 0, hi = Q;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (bq[mid].x < xlo) lo = mid + 1; else hi = mid;
+        }
+        start = min(lo, Q - 1) / TILE;
+    }
+    int left = start - 1, right = start;       // next unvisited tile on each side
+    bool left_open = prune != 0, right_open = true;
+    if (!prune) left = -1;
+
+    while (true) {
+        // ---- pick the next tile: the side whose x gap to the query range is smaller; prune by the gap --------------
+        int tsel = -1;
+        {
+            const float thr_max = blk[2];
+            float gl = FLT_MAX, gr = FLT_MAX;
+            if (left_open && left >= 0) {
+                const float xl = bq[min((left + 1) * TILE, Q) - 1].x;      // largest x of the left tile
+                gl = fmaxf(xlo - xl, 0.f);
+                if (thr_max < FLT_MAX && gl * gl > thr_max) { left_open = false; gl = FLT_MAX; }
+            } else left_open = false;
+            if (right_open && right < ntiles) {
+                const float xr = bq[right * TILE].x;                        // smallest x of the right tile
+                gr = prune ? fmaxf(xr - xhi, 0.f) : 0.f;
+                if (thr_max < FLT_MAX && gr * gr > thr_max) { right_open = false; gr = FLT_MAX; }
+            } else right_open = false;
+            if (!left_open && !right_open) break;
+            if (right_open && (!left_open || gr <= gl)) tsel = right++; else tsel = left--;
+        }
+        const int q0 = tsel * TILE;
         const int cnt = min(TILE, Q - q0);
         __syncthreads();
-        for (int t = threadIdx.x; t < cnt; t += THREADS) {
-            const float* s = bq + (size_t)(q0 + t) * 3;
-            tile[t] = make_float4(s[0], s[1], s[2], 0.f);
+        if (tid == 0) qq_max_bits = 0;
+        __syncthreads();
+        float qmax = 0.f;
+        for (int t = tid; t < cnt; t += THREADS) {
+            const float4 s = bq[q0 + t];
+            const float qq = fmaf(s.z, s.z, fmaf(s.y, s.y, s.x * s.x));
+            tile[t] = make_float4(-2.f * s.x, -2.f * s.y, -2.f * s.z, qq);
+            tile_idx[t] = __float_as_int(s.w);
+            qmax = fmaxf(qmax, qq);
+        }
+        if (tid < STEP) tile[cnt + tid] = make_float4(0.f, 0.f, 0.f, FLT_MAX);   // never-matching sentinels
+        atomicMax(&qq_max_bits, __float_as_int(qmax));     // non-negative floats order like their bit patterns
+        __syncthreads();
+        const float qq_max = __int_as_float(qq_max_bits);
+        float margin[QPT];
+#pragma unroll
+        for (int u = 0; u < QPT; ++u) {
+            margin[u] = 1e-6f * (qr[u].pp + qq_max) + 1e-37f;
+            qr[u].set_threshold(margin[u]);
+        }
+        // STEP candidates per iteration, then one warp-uniform vote: queues are drained by the whole warp together
+        // (a lane draining alone would serialise the ~70-instruction insertion across the 32 lanes).
+        for (int t0 = 0; t0 < cnt; t0 += STEP) {
+#pragma unroll
+            for (int tt = 0; tt < STEP; ++tt) {
+                const float4 c = tile[t0 + tt];
+#pragma unroll
+                for (int u = 0; u < QPT; ++u) {
+                    const float s = fmaf(qr[u].x, c.x, fmaf(qr[u].y, c.y, fmaf(qr[u].z, c.z, c.w)));
+                    if (s < qr[u].thr) {
+                        queue[u][qr[u].cnt * THREADS + tid] = (unsigned short)(t0 + tt);
+                        ++qr[u].cnt;
+                    }
+                }
+            }
+            int fullest = qr[0].cnt;
+#pragma unroll
+            for (int u = 1; u < QPT; ++u) fullest = max(fullest, qr[u].cnt);
+            if (__any_sync(0xffffffffu, fullest > QCAP - STEP)) {
+#pragma unroll
+                for (int u = 0; u < QPT; ++u) qr[u].drain(tile, tile_idx, &queue[u][tid], margin[u]);
+            }
+        }
+        float tmax = 0.f;
+#pragma unroll
+        for (int u = 0; u < QPT; ++u) {
+            qr[u].drain(tile, tile_idx, &queue[u][tid], margin[u]);
+            tmax = fmaxf(tmax, qr[u].top.d[K - 1]);
+        }
+        // CTA-wide max of the k-th best distances (the pruning bound for the next tile)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+        if (lane_id() == 0) red[warp_id()][2] = tmax;
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < THREADS / 32; ++w) tmax = fmaxf(tmax, red[w][2]);
+            blk[2] = tmax;
         }
         __syncthreads();
-        if (K > 0) {
-#pragma unroll 4
-            for (int t = 0; t < cnt; ++t) {
-                const float4 c = tile[t];
-                const float dx = px - c.x, dy = py - c.y, dz = pz - c.z;
-                const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                if (d < top.d[K > 0 ? K - 1 : 0]) top.insert(d, q0 + t);
-            }
-        } else {
-#pragma unroll 8
-            for (int t = 0; t < cnt; ++t) {
-                const float4 c = tile[t];
-                const float dx = px - c.x, dy = py - c.y, dz = pz - c.z;
-                const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                if (d < best) { best = d; besti = q0 + t; }
-            }
-        }
     }
-    if (!active) return;
-    const size_t o = (size_t)batch * P + p;
-    if (K > 0) {
-        min_d[o] = top.d[0];
-        min_i[o] = top.i[0];
+#pragma unroll
+    for (int u = 0; u < QPT; ++u) {
+        if (pidx[u] >= P) continue;
+        const size_t o = (size_t)batch * P + orig[u];
+        min_d[o] = qr[u].top.d[0];
+        min_i[o] = qr[u].top.i[0];
 #pragma unroll
         for (int s = 0; s < K; ++s)
-            if (s < k_out) knn[o * k_out + s] = top.i[s];
-    } else {
-        min_d[o] = best;
-        min_i[o] = besti;
+            if (s < k_out) knn[o * k_out + s] = qr[u].top.i[s];
     }
 }
 
@@ -145,9 +331,29 @@ __global__ void __launch_bounds__(256) k_chamfer_bwd(const float* __restrict__ a
 }
 
 template <int K>
-static void launch_nn(const float* a, const float* b, int B, int P, int Q, float* min_d, int32_t* min_i, int32_t* knn,
-                      int k, cudaStream_t s) {
-    k_nn<K><<<dim3(ceil_div(P, THREADS), B), THREADS, 0, s>>>(a, b, P, Q, min_d, min_i, knn, k);
+static void launch_nn(const float4* a, const float4* b, int B, int P, int Q, int prune, float* min_d, int32_t* min_i,
+                      int32_t* knn, int k, cudaStream_t s) {
+    k_nn<K><<<dim3(ceil_div(P, THREADS * QPT), B), THREADS, 0, s>>>(a, b, P, Q, prune, min_d, min_i, knn, k);
+}
+
+static int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
+
+// packs (and x-sorts, when the cloud fits the shared-memory sort) B clouds of P points into float4 records
+static bool pack_cloud(const float* pts, int B, int P, float4* out, cudaStream_t s) {
+    if (P <= SORT_MAX) {
+        const int N2 = max(next_pow2(P), 2);
+        const size_t smem = (size_t)N2 * 6;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_sort_x, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_MAX * 6);
+            attr_set = true;
+        }
+        k_sort_x<<<B, 1024, smem, s>>>(pts, P, N2, out);
+        return true;
+    }
+    const long long n = (long long)B * P;
+    k_pack<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(pts, n, P, out);
+    return false;
 }
 
 }  // namespace chamfer
@@ -156,19 +362,37 @@ static void launch_nn(const float* a, const float* b, int B, int P, int Q, float
 using namespace mrb;
 using namespace mrb::chamfer;
 
-extern "C" int mrb_knn_fwd(const float* a, const float* b, int B, int P, int Q, int k, float* min_d, int32_t* min_i,
-                           int32_t* knn, void* stream_) {
-    MRB_REQUIRE(a && b && min_d && min_i, "knn_fwd: null pointer");
+extern "C" long long mrb_knn_workspace_bytes(int B, int P, int Q) {
+    if (B < 0 || P < 0 || Q < 0) return -1;
+    return (long long)sizeof(float4) * ((long long)B * P + (long long)B * Q) + 256;
+}
+
+extern "C" int mrb_knn_fwd(const float* a, const float* b, int B, int P, int Q, int k, float* min_d_a, int32_t* min_i_a,
+                           int32_t* knn_a, float* min_d_b, int32_t* min_i_b, int32_t* knn_b, void* workspace,
+                           void* stream_) {
+    MRB_REQUIRE(a && b && workspace, "knn_fwd: null pointer");
     MRB_REQUIRE(k >= 0 && k <= 16, "knn_fwd: k must be in [0, 16], got %d", k);
-    MRB_REQUIRE(k == 0 || knn, "knn_fwd: knn output missing");
-    MRB_REQUIRE(k <= Q, "knn_fwd: k = %d exceeds the number of candidate points %d", k, Q);
-    MRB_REQUIRE(Q > 0 || P == 0, "knn_fwd: empty candidate cloud");
-    if (B == 0 || P == 0) return MRB_OK;
+    MRB_REQUIRE((min_d_a && min_i_a) || (min_d_b && min_i_b), "knn_fwd: no output requested");
+    MRB_REQUIRE(k == 0 || ((!min_d_a || knn_a) && (!min_d_b || knn_b)), "knn_fwd: knn output missing");
+    MRB_REQUIRE(k <= Q && k <= P, "knn_fwd: k = %d exceeds a cloud size (%d, %d)", k, P, Q);
+    MRB_REQUIRE(B == 0 || (P > 0 && Q > 0), "knn_fwd: empty cloud");
+    MRB_REQUIRE(B <= 65535, "knn_fwd: batch too large");
+    if (B == 0) return MRB_OK;
     cudaStream_t s = (cudaStream_t)stream_;
-    if (k == 0) launch_nn<0>(a, b, B, P, Q, min_d, min_i, knn, k, s);
-    else if (k <= 4) launch_nn<4>(a, b, B, P, Q, min_d, min_i, knn, k, s);
-    else if (k <= 10) launch_nn<10>(a, b, B, P, Q, min_d, min_i, knn, k, s);
-    else launch_nn<16>(a, b, B, P, Q, min_d, min_i, knn, k, s);
+    float4* pa = reinterpret_cast<float4*>(((uintptr_t)workspace + 15) & ~(uintptr_t)15);
+    float4* pb = pa + (size_t)B * P;
+    const bool sa = pack_cloud(a, B, P, pa, s);
+    const bool sb = pack_cloud(b, B, Q, pb, s);
+#define MRB_NN(KK)                                                                                        \
+    do {                                                                                                  \
+        if (min_d_a) launch_nn<KK>(pa, pb, B, P, Q, sb ? 1 : 0, min_d_a, min_i_a, knn_a, k, s);           \
+        if (min_d_b) launch_nn<KK>(pb, pa, B, Q, P, sa ? 1 : 0, min_d_b, min_i_b, knn_b, k, s);           \
+    } while (0)
+    if (k <= 1) MRB_NN(1);
+    else if (k <= 4) MRB_NN(4);
+    else if (k <= 10) MRB_NN(10);
+    else MRB_NN(16);
+#undef MRB_NN
     return check_launch("knn_fwd");
 }
 

@@ -440,8 +440,9 @@ class _Chamfer(torch.autograd.Function):
         iq = torch.empty(B, Q, dtype=torch.int32, device=dev)
         kp = torch.empty(B, P, k, dtype=torch.int32, device=dev) if k else None
         kq = torch.empty(B, Q, k, dtype=torch.int32, device=dev) if k else None
-        _lib.call("mrb_knn_fwd", _lib.ptr(pc), _lib.ptr(qc), B, P, Q, k, _lib.ptr(dp), _lib.ptr(ip), _lib.ptr(kp))
-        _lib.call("mrb_knn_fwd", _lib.ptr(qc), _lib.ptr(pc), B, Q, P, k, _lib.ptr(dq), _lib.ptr(iq), _lib.ptr(kq))
+        ws = torch.empty(_lib.load().mrb_knn_workspace_bytes(B, P, Q), dtype=torch.uint8, device=dev)
+        _lib.call("mrb_knn_fwd", _lib.ptr(pc), _lib.ptr(qc), B, P, Q, k, _lib.ptr(dp), _lib.ptr(ip), _lib.ptr(kp),
+                  _lib.ptr(dq), _lib.ptr(iq), _lib.ptr(kq), _lib.ptr(ws))
         acc = torch.empty(2, dtype=torch.float64, device=dev)
         sums = torch.empty(2, dtype=torch.float32, device=dev)
         _lib.call("mrb_sum_scaled", _lib.ptr(dp), B * P, 1.0, _lib.ptr(acc), _lib.ptr(sums))
