@@ -80,6 +80,19 @@ int mrb_segment_ids(const int32_t* offsets, int nseg, int n, int32_t* ids, void*
 int mrb_sgemm(int transA, int transB, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
               float beta, float* C, int ldc, void* stream);
 
+/* Tensor-core path (tcgen05.mma kind::tf32, accumulators in TMEM, 3xTF32 split => fp32-level accuracy) for the
+ * activation x weight products  C[M x N] = A[M x K] * B[K x N]  with M = number of vertices.
+ *   mrb_gemm_tc_pack  builds the weight image once per call: logical element B(k, n) = src[k*stride_k + n*stride_n],
+ *                     optionally taken from a second source beyond `split_at` along n (split_axis = 1) or k
+ *                     (split_axis = 2) -- this is how [W0 | W1] (GraphConv forward, layers.py:54,57) and its transpose
+ *                     (backward) are formed without a concatenation.  image: mrb_gemm_tc_image_bytes(K, N) bytes, 16 B aligned.
+ *   mrb_gemm_tc       A fp32 row-major (lda >= K), C fp32 row-major (ldc >= N).
+ */
+long long mrb_gemm_tc_image_bytes(int K, int N);
+int mrb_gemm_tc_pack(const float* src0, const float* src1, long long stride_k, long long stride_n, int split_axis,
+                     int split_at, int K, int N, void* image, void* stream);
+int mrb_gemm_tc(const float* A, int lda, int M, int K, const void* image, int N, float* C, int ldc, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * VertexAlign -- replaces VertexAlign.forward / single_projection / project, reference meshRCNN/layers.py:521-613,
  * with the reference's exact (non-bilinear) semantics: out[v,c] = fmap[img,c,x1,y1] * [x2>x1 && y2>y1].

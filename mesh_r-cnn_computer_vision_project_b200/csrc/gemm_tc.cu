@@ -1,0 +1,364 @@
+// GraphConv / linear projections on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+//   C[M x N] = A[M x K] * B[K x N]      A: fp32 activations, row-major (lda), M = number of vertices (50k .. 7M)
+//                                       B: weights, pre-packed once per call into a K-major, 128B-swizzled, split image
+//
+// Replaces the cuBLAS sgemm call sites of the reference (meshRCNN/layers.py:54,57 torch.mm(x, w0/w1), nn.Linear at
+// :93,155,230,255,335) and their autograd transposes.  fp32 parity (rtol 1e-4) rules out a single TF32/BF16 pass, so
+// the product is evaluated as a 3xTF32 split on the tensor pipe:  a = a_hi + a_lo (both tf32-representable),
+//   a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi          (error ~2^-21 relative, fp32 accumulate in TMEM)
+// Arithmetic intensity at N <= 256 is below the B200 ridge, so the kernel is HBM-bound by design: A is read once,
+// C written once, and the weight image (<= 0.8 MB) streams from L2.
+//
+// CTA = one 128-row M tile x one N tile (<= 256 columns).  Warp roles (192 threads):
+//   warps 0-3  producers: coalesced fp32 loads of the A chunk (128 x 32), hi/lo split, swizzled st.shared,
+//              fence.proxy.async, mbarrier arrive;   afterwards the epilogue: tcgen05.ld -> smem transpose -> coalesced C
+//   warp 4     lane 0 issues tcgen05.mma (kind::tf32, M=128, N=NT, K=8), tcgen05.commit frees the stage / signals the epilogue;
+//              the whole warp owns the TMEM allocation
+//   warp 5     lane 0 streams the packed weight chunk with cp.async.bulk (TMA bulk copy) onto the stage's mbarrier
+#include "common.cuh"
+#include "../../include/meshrcnn_b200.h"
+
+namespace mrb {
+namespace gemmtc {
+
+constexpr int BM = 128;            // rows per CTA (UMMA M)
+constexpr int BK = 32;             // fp32 elements per K chunk = one 128-byte swizzle row
+constexpr int STAGES = 2;
+constexpr int NT_MAX = 256;        // max columns per CTA (UMMA N)
+constexpr int A_BYTES = BM * BK * 4;                   // 16 KB per (hi | lo) tile
+constexpr int B_BYTES_MAX = NT_MAX * BK * 4;           // 32 KB per (hi | lo) tile
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES_MAX;   // 96 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int THREADS = 192;
+
+// byte offset of element (row, k) inside a K-major SWIZZLE_128B tile whose rows are 32 fp32 wide
+__host__ __device__ __forceinline__ int swz(int row, int k) {
+    return (row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 2) ^ (row & 7)) & 7) << 4) + (k & 3) * 4;
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO(=1)<<16 |
+// SBO(=1024>>4)<<32 | version(1)<<46 | layout SWIZZLE_128B(2)<<61
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 (1<<4), A=B=TF32 (2<<7, 2<<10), K-major both, N>>3 @17, M>>4 @24
+__device__ __forceinline__ uint32_t umma_idesc(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+struct Params {
+    const float* A;
+    int lda, M, K;
+    const unsigned char* image;   // [n_tile][chunk][hi|lo][NT rows][128 B]
+    int N, NT, nchunks, tmem_cols;   // tmem_cols: columns of one accumulator
+    int nacc;                        // accumulators used round-robin over the K chunks (bounds the fp32 chain length)
+    float* C;
+    int ldc;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(Params p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);   // full[2], empty[2], tmem_full
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    const uint32_t tfull_bar = bar_base + 8u * (2 * STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM;
+    const int ntile = blockIdx.y;
+    const int NT = p.NT;
+    const int b_bytes = NT * BK * 4;     // one (hi | lo) weight tile
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 128 + 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tfull_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(p.tmem_cols * p.nacc)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp < 4) {
+        // ===== A producers ======================================================================================
+        const int r0 = warp * 32;
+        for (int c = 0; c < p.nchunks; ++c) {
+            const int s = c & 1, use = c >> 1;
+            if (use > 0) mbar_wait(empty_bar(s), (use - 1) & 1);
+            unsigned char* a_hi = smem + s * STAGE_BYTES;
+            unsigned char* a_lo = a_hi + A_BYTES;
+            const int k = c * BK + lane;
+            const bool kin = k < p.K;
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) {
+                const int row = r0 + i;
+                const int gm = m0 + row;
+                float v = 0.f;
+                if (kin && gm < p.M) v = __ldg(p.A + (size_t)gm * p.lda + k);
+                const float hi = tf32_rna(v);
+                const float lo = tf32_rna(v - hi);
+                const int off = swz(row, lane);
+                *reinterpret_cast<float*>(a_hi + off) = hi;
+                *reinterpret_cast<float*>(a_lo + off) = lo;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA
+            mbar_arrive(full_bar(s));
+        }
+        // ===== epilogue: TMEM -> registers -> smem transpose -> coalesced global rows ==================================
+        mbar_wait(tfull_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float* stage_t = reinterpret_cast<float*>(smem) + warp * (32 * 33);   // stage buffers are free now
+        const int n0 = ntile * NT;
+        for (int c0 = 0; c0 < NT; c0 += 32) {
+            float acc[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+            for (int a = 0; a < p.nacc; ++a) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * p.tmem_cols + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
+                      "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+                      "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(v[j]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) stage_t[lane * 33 + j] = acc[j];
+            __syncwarp();
+            const int col = n0 + c0 + lane;
+            if (c0 + lane < NT && col < p.N) {
+#pragma unroll 4
+                for (int r = 0; r < 32; ++r) {
+                    const int gm = m0 + warp * 32 + r;
+                    if (gm < p.M) p.C[(size_t)gm * p.ldc + col] = stage_t[r * 33 + lane];
+                }
+            }
+            __syncwarp();
+        }
+    } else if (warp == 4) {
+        // ===== MMA issuer ========================================================================================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(NT);
+            for (int c = 0; c < p.nchunks; ++c) {
+                const int s = c & 1, use = c >> 1;
+                mbar_wait(full_bar(s), use & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_BYTES;
+                const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + b_bytes;
+#pragma unroll
+                for (int kk = 0; kk < BK / 8; ++kk) {
+                    const uint64_t dah = umma_desc(a_hi + kk * 32), dal = umma_desc(a_lo + kk * 32);
+                    const uint64_t dbh = umma_desc(b_hi + kk * 32), dbl = umma_desc(b_lo + kk * 32);
+                    const uint32_t d = tmem_d + (uint32_t)((c % p.nacc) * p.tmem_cols);
+                    umma_tf32(d, dal, dbh, idesc, (c >= p.nacc) || kk != 0);
+                    umma_tf32(d, dah, dbl, idesc, 1);
+                    umma_tf32(d, dah, dbh, idesc, 1);
+                }
+                umma_commit(empty_bar(s));                 // stage reusable once these MMAs retire
+            }
+            umma_commit(tfull_bar);                        // accumulator complete -> epilogue
+        }
+        __syncwarp();
+    } else {
+        // ===== weight-chunk TMA (bulk copy) producer =======================================================================
+        if (lane == 0) {
+            const unsigned char* img = p.image + (size_t)ntile * p.nchunks * 2 * b_bytes;
+            for (int c = 0; c < p.nchunks; ++c) {
+                const int s = c & 1, use = c >> 1;
+                if (use > 0) mbar_wait(empty_bar(s), (use - 1) & 1);
+                const uint32_t dst = smem_base + s * STAGE_BYTES + 2 * A_BYTES;
+                mbar_expect_tx(full_bar(s), 2 * b_bytes);
+                bulk_g2s(dst, img + (size_t)c * 2 * b_bytes, b_bytes, full_bar(s));
+                bulk_g2s(dst + b_bytes, img + (size_t)c * 2 * b_bytes + b_bytes, b_bytes, full_bar(s));
+            }
+        }
+        __syncwarp();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(p.tmem_cols * p.nacc) : "memory");
+    }
+}
+
+// Weight image: element (k, n) of the logical K x N operand, read through generic strides from up to two sources
+// (so that [W0 | W1] and its transpose never have to be concatenated in memory), split into tf32 hi / lo and written
+// in the exact shared-memory layout of the main kernel (zero padded in K and N).
+struct PackParams {
+    const float* src0;
+    const float* src1;
+    long long sk, sn;     // strides (elements) of k and n in the sources
+    int split_axis;       // 0: single source; 1: n >= split_at comes from src1 (n - split_at); 2: same along k
+    int split_at;
+    int K, N, NT, nchunks, ntiles;
+    unsigned char* image;
+};
+
+__global__ void k_pack_b(PackParams p) {
+    const long long total = (long long)p.ntiles * p.nchunks * p.NT * BK;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int kl = (int)(t % BK);
+    const int nl = (int)((t / BK) % p.NT);
+    const int c = (int)((t / ((long long)BK * p.NT)) % p.nchunks);
+    const int tile = (int)(t / ((long long)BK * p.NT * p.nchunks));
+    const int k = c * BK + kl, n = tile * p.NT + nl;
+    float v = 0.f;
+    if (k < p.K && n < p.N) {
+        const float* src = p.src0;
+        int kk = k, nn = n;
+        if (p.split_axis == 1 && n >= p.split_at) { src = p.src1; nn = n - p.split_at; }
+        if (p.split_axis == 2 && k >= p.split_at) { src = p.src1; kk = k - p.split_at; }
+        v = src[kk * p.sk + nn * p.sn];
+    }
+    const float hi = tf32_rna(v), lo = tf32_rna(v - hi);
+    const size_t tile_bytes = (size_t)p.NT * BK * 4;
+    unsigned char* base = p.image + ((size_t)tile * p.nchunks + c) * 2 * tile_bytes;
+    const int off = swz(nl, kl);
+    *reinterpret_cast<float*>(base + off) = hi;
+    *reinterpret_cast<float*>(base + tile_bytes + off) = lo;
+}
+
+struct Plan {
+    int NT, ntiles, nchunks, tmem_cols, nacc;
+    size_t image_bytes;
+};
+
+static Plan make_plan(int K, int N) {
+    Plan pl;
+    pl.ntiles = (N + NT_MAX - 1) / NT_MAX;
+    const int per = (N + pl.ntiles - 1) / pl.ntiles;
+    pl.NT = ((per + 15) / 16) * 16;
+    pl.nchunks = (K + BK - 1) / BK;
+    int cols = 32;
+    while (cols < pl.NT) cols <<= 1;
+    pl.tmem_cols = cols;
+    // The tensor-core fp32 accumulate truncates, so the error of one accumulator grows linearly with the number of MMAs
+    // chained into it; long reductions (K > 512, e.g. the 3840 -> 128 bottleneck) are spread over up to 4 accumulators
+    // (512 TMEM columns) that the epilogue adds on the CUDA cores.
+    pl.nacc = 1;
+    if (pl.nchunks > 16) {
+        const int want = min(4, min(512 / cols, (pl.nchunks + 15) / 16));
+        while (pl.nacc * 2 <= want) pl.nacc *= 2;      // TMEM allocations are powers of two
+    }
+    pl.image_bytes = (size_t)pl.ntiles * pl.nchunks * 2 * pl.NT * BK * 4;
+    return pl;
+}
+
+}  // namespace gemmtc
+}  // namespace mrb
+
+using namespace mrb;
+using namespace mrb::gemmtc;
+
+extern "C" long long mrb_gemm_tc_image_bytes(int K, int N) {
+    if (K <= 0 || N <= 0) return -1;
+    return (long long)make_plan(K, N).image_bytes;
+}
+
+extern "C" int mrb_gemm_tc_pack(const float* src0, const float* src1, long long stride_k, long long stride_n,
+                                int split_axis, int split_at, int K, int N, void* image, void* stream_) {
+    MRB_REQUIRE(src0 && image && K > 0 && N > 0, "gemm_tc_pack: bad arguments");
+    MRB_REQUIRE(split_axis == 0 || src1, "gemm_tc_pack: second source missing");
+    MRB_REQUIRE(((uintptr_t)image & 15) == 0, "gemm_tc_pack: image must be 16-byte aligned");
+    const Plan pl = make_plan(K, N);
+    PackParams p;
+    p.src0 = src0; p.src1 = src1; p.sk = stride_k; p.sn = stride_n; p.split_axis = split_axis; p.split_at = split_at;
+    p.K = K; p.N = N; p.NT = pl.NT; p.nchunks = pl.nchunks; p.ntiles = pl.ntiles;
+    p.image = (unsigned char*)image;
+    const long long total = (long long)pl.ntiles * pl.nchunks * pl.NT * BK;
+    k_pack_b<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream_>>>(p);
+    return check_launch("gemm_tc_pack");
+}
+
+extern "C" int mrb_gemm_tc(const float* A, int lda, int M, int K, const void* image, int N, float* C, int ldc,
+                           void* stream_) {
+    MRB_REQUIRE(A && image && C, "gemm_tc: null pointer");
+    MRB_REQUIRE(M >= 0 && K > 0 && N > 0 && lda >= K && ldc >= N, "gemm_tc: bad shape M=%d K=%d N=%d lda=%d ldc=%d", M, K, N,
+                lda, ldc);
+    MRB_REQUIRE(((uintptr_t)image & 15) == 0, "gemm_tc: image must be 16-byte aligned");
+    if (M == 0) return MRB_OK;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) {
+            set_error("gemm_tc: cannot reserve %d bytes of shared memory: %s", SMEM_BYTES, cudaGetErrorString(e));
+            return MRB_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    const Plan pl = make_plan(K, N);
+    Params p;
+    p.A = A; p.lda = lda; p.M = M; p.K = K; p.image = (const unsigned char*)image; p.N = N; p.NT = pl.NT;
+    p.nchunks = pl.nchunks; p.tmem_cols = pl.tmem_cols; p.nacc = pl.nacc; p.C = C; p.ldc = ldc;
+    dim3 grid(ceil_div(M, BM), pl.ntiles);
+    k_gemm_tc<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(p);
+    return check_launch("gemm_tc");
+}

@@ -124,6 +124,11 @@ def _gemm(ta: bool, tb: bool, M: int, N: int, K: int, a_ptr: int, lda: int, b_pt
     _lib.call("mrb_sgemm", int(ta), int(tb), M, N, K, a_ptr, lda, b_ptr, ldb, float(beta), c_ptr, ldc)
 
 
+def _use_tc(K: int, N: int) -> bool:
+    """Products wide enough for a UMMA tile run on tcgen05; skinny heads (N = 3 / 6) stay on the CUDA-core kernel."""
+    return N >= 16 and K >= 16
+
+
 class _MatMul(torch.autograd.Function):
     """y = x @ (w^T if trans_w else w)."""
 
@@ -134,7 +139,11 @@ class _MatMul(torch.autograd.Function):
         M, K = x.shape
         N = w.shape[0] if trans_w else w.shape[1]
         y = torch.empty(M, N, dtype=torch.float32, device=x.device)
-        _gemm(False, trans_w, M, N, K, _lib.ptr(x), K, _lib.ptr(w), w.shape[1], 0.0, _lib.ptr(y), N)
+        if _use_tc(K, N):
+            img = tc_pack(w, None, 1 if trans_w else N, K if trans_w else 1, 0, 0, K, N)
+            tc_gemm(_lib.ptr(x), K, M, K, img, N, _lib.ptr(y), N)
+        else:
+            _gemm(False, trans_w, M, N, K, _lib.ptr(x), K, _lib.ptr(w), w.shape[1], 0.0, _lib.ptr(y), N)
         ctx.save_for_backward(x, w)
         ctx.trans_w = trans_w
         return y
@@ -148,8 +157,12 @@ class _MatMul(torch.autograd.Function):
         gx = gw = None
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)
-            # gx = gy @ w (trans_w) or gy @ w^T
-            _gemm(False, not ctx.trans_w, M, K, N, _lib.ptr(gy), N, _lib.ptr(w), w.shape[1], 0.0, _lib.ptr(gx), K)
+            # gx = gy @ w (trans_w) or gy @ w^T :  logical B(k = out index, n = in index)
+            if _use_tc(N, K):
+                img = tc_pack(w, None, K if ctx.trans_w else 1, 1 if ctx.trans_w else N, 0, 0, N, K)
+                tc_gemm(_lib.ptr(gy), N, M, N, img, K, _lib.ptr(gx), K)
+            else:
+                _gemm(False, not ctx.trans_w, M, K, N, _lib.ptr(gy), N, _lib.ptr(w), w.shape[1], 0.0, _lib.ptr(gx), K)
         if ctx.needs_input_grad[1]:
             gw = torch.empty_like(w)
             if ctx.trans_w:   # w: N x K ; gw = gy^T @ x
@@ -215,8 +228,12 @@ class _GraphConv(torch.autograd.Function):
         D = w0.shape[1]
         y = torch.empty(n, 2 * D, dtype=torch.float32, device=x.device)
         yp = _lib.ptr(y)
-        _gemm(False, False, n, D, K, _lib.ptr(x), K, _lib.ptr(w0), D, 0.0, yp, 2 * D)
-        _gemm(False, False, n, D, K, _lib.ptr(x), K, _lib.ptr(w1), D, 0.0, yp + 4 * D, 2 * D)
+        if _use_tc(K, 2 * D):      # one tensor-core pass over x for [x W0 | x W1]
+            img = tc_pack(w0, w1, D, 1, 1, D, K, 2 * D)
+            tc_gemm(_lib.ptr(x), K, n, K, img, 2 * D, yp, 2 * D)
+        else:
+            _gemm(False, False, n, D, K, _lib.ptr(x), K, _lib.ptr(w0), D, 0.0, yp, 2 * D)
+            _gemm(False, False, n, D, K, _lib.ptr(x), K, _lib.ptr(w1), D, 0.0, yp + 4 * D, 2 * D)
         out = torch.empty(n, D, dtype=torch.float32, device=x.device)
         _gather(topo.rowptr, topo.col, n, yp, 2 * D, yp + 4 * D, 2 * D, D, True, _lib.ptr(out), D)
         ctx.save_for_backward(x, w0, w1, out)
@@ -237,8 +254,12 @@ class _GraphConv(torch.autograd.Function):
         gx = gw0 = gw1 = None
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)
-            _gemm(False, True, n, K, D, gp, 2 * D, _lib.ptr(w0), D, 0.0, _lib.ptr(gx), K)
-            _gemm(False, True, n, K, D, gp + 4 * D, 2 * D, _lib.ptr(w1), D, 1.0, _lib.ptr(gx), K)
+            if _use_tc(2 * D, K):  # gx = [gz | A^T gz] @ [W0 | W1]^T in one pass
+                img = tc_pack(w0, w1, 1, D, 2, D, 2 * D, K)
+                tc_gemm(gp, 2 * D, n, 2 * D, img, K, _lib.ptr(gx), K)
+            else:
+                _gemm(False, True, n, K, D, gp, 2 * D, _lib.ptr(w0), D, 0.0, _lib.ptr(gx), K)
+                _gemm(False, True, n, K, D, gp + 4 * D, 2 * D, _lib.ptr(w1), D, 1.0, _lib.ptr(gx), K)
         if ctx.needs_input_grad[1]:
             gw0 = torch.empty_like(w0)
             _gemm(True, False, K, D, n, _lib.ptr(x), K, gp, 2 * D, 0.0, _lib.ptr(gw0), D)
@@ -537,3 +558,21 @@ def compute_normals(pt: Tensor, knn: Tensor) -> Tensor:
     out = torch.empty(B, P, 3, dtype=torch.float32, device=pt.device)
     _lib.call("mrb_normals_fwd", _lib.ptr(pc), _lib.ptr(knn), B, P, knn.shape[2], _lib.ptr(out))
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# tensor-core projections (tcgen05): weight image packing + GEMM
+# ----------------------------------------------------------------------------------------------------------
+def tc_pack(src0: Tensor, src1: Optional[Tensor], stride_k: int, stride_n: int, split_axis: int, split_at: int,
+            K: int, N: int) -> Tensor:
+    """Packs the logical K x N weight operand B(k, n) = src[k*stride_k + n*stride_n] (two sources when split) into the
+    tf32 hi/lo, K-major, 128B-swizzled image the tcgen05 kernel streams with TMA bulk copies."""
+    nbytes = _lib.load().mrb_gemm_tc_image_bytes(K, N)
+    image = torch.empty(nbytes, dtype=torch.uint8, device=src0.device)
+    _lib.call("mrb_gemm_tc_pack", _lib.ptr(src0), _lib.ptr(src1), stride_k, stride_n, split_axis, split_at, K, N,
+              _lib.ptr(image))
+    return image
+
+
+def tc_gemm(a_ptr: int, lda: int, M: int, K: int, image: Tensor, N: int, c_ptr: int, ldc: int) -> None:
+    _lib.call("mrb_gemm_tc", a_ptr, lda, M, K, _lib.ptr(image), N, c_ptr, ldc)

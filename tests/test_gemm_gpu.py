@@ -1,0 +1,58 @@
+"""tcgen05 (3xTF32) projection kernel vs fp64 matmul: fp32-level accuracy (rtol 1e-4 of the north star with margin)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(M, K, N, lda_pad=0, ldc_pad=0, split=None, transposed_src=False, seed=0):
+    from meshrcnn_b200 import _lib, functional as F_
+    g = torch.Generator().manual_seed(seed)
+    a_full = torch.randn(M, K + lda_pad, generator=g)
+    a = a_full[:, :K]
+    if split is None:
+        w = torch.randn(N, K, generator=g) if transposed_src else torch.randn(K, N, generator=g)
+        wl = w.t() if transposed_src else w
+        wd = w.cuda()
+        sk, sn = (1, K) if transposed_src else (N, 1)
+        img = F_.tc_pack(wd, None, sk, sn, 0, 0, K, N)
+    elif split == "n":          # [W0 | W1], each K x N/2
+        w0, w1 = torch.randn(K, N // 2, generator=g), torch.randn(K, N // 2, generator=g)
+        wl = torch.cat([w0, w1], 1)
+        w0d, w1d = w0.cuda(), w1.cuda()
+        img = F_.tc_pack(w0d, w1d, N // 2, 1, 1, N // 2, K, N)
+    else:                       # [W0 | W1]^T : logical (k, n) = Wcat[n][k], W* are N x K/2
+        w0, w1 = torch.randn(N, K // 2, generator=g), torch.randn(N, K // 2, generator=g)
+        wl = torch.cat([w0, w1], 1).t()
+        w0d, w1d = w0.cuda(), w1.cuda()
+        img = F_.tc_pack(w0d, w1d, 1, K // 2, 2, K // 2, K, N)
+    ad = a_full.cuda()
+    c = torch.full((M, N + ldc_pad), -7.0, device="cuda")
+    F_.tc_gemm(_lib.ptr(ad), K + lda_pad, M, K, img, N, _lib.ptr(c), N + ldc_pad)
+    torch.cuda.synchronize()
+    want = a.double() @ wl.double()
+    got = c[:, :N].cpu().double()
+    scale = float(want.abs().max())
+    err = float((got - want).abs().max())
+    assert err <= 1e-5 * scale, (M, K, N, err, scale)    # tensor-core fp32 accumulation truncates: ~6e-8 * (#chained MMAs)
+    if ldc_pad:
+        assert bool((c[:, N:] == -7.0).all())          # no write outside the N columns
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 32, 16), (128, 32, 256), (1000, 131, 256), (333, 259, 256), (4097, 387, 256),
+                                   (50353, 131, 256), (257, 128, 128), (100, 3840, 128), (5, 8, 16)])
+def test_tc_gemm_shapes(lib, M, K, N):
+    _check(M, K, N)
+
+
+def test_tc_gemm_strides_and_padding(lib):
+    _check(300, 131, 128, lda_pad=5, ldc_pad=3)
+    _check(300, 256, 131, ldc_pad=1)                   # N not a multiple of 16 (backward of a 131-wide layer)
+    _check(700, 256, 387)                              # two N tiles of 208
+    _check(700, 256, 259, transposed_src=True)
+
+
+def test_tc_gemm_split_sources(lib):
+    _check(513, 131, 256, split="n")                   # GraphConv forward  x @ [W0 | W1]
+    _check(513, 256, 131, split="k")                   # GraphConv backward gy @ [W0 | W1]^T
+    _check(513, 256, 387, split="k")
