@@ -140,27 +140,36 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(Params p) {
     if (warp < 4) {
         // ===== A producers ======================================================================================
         const int r0 = warp * 32;
+        // All 32 row segments of the next chunk are requested before the current one is converted, so every producer
+        // thread keeps 32 independent 128-byte-coalesced loads in flight across the stage hand-over (the loop is
+        // load-latency bound otherwise: the MMA needs ~0.8 us per chunk, an L2/HBM round trip takes about as long).
+        float v[32];
+        auto load_chunk = [&](int c) {
+            const int k = c * BK + lane;
+            const bool kin = k < p.K;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int gm = m0 + r0 + i;
+                v[i] = (kin && gm < p.M) ? __ldg(p.A + (size_t)gm * p.lda + k) : 0.f;
+            }
+        };
+        load_chunk(0);
         for (int c = 0; c < p.nchunks; ++c) {
             const int s = c & 1, use = c >> 1;
             if (use > 0) mbar_wait(empty_bar(s), (use - 1) & 1);
             unsigned char* a_hi = smem + s * STAGE_BYTES;
             unsigned char* a_lo = a_hi + A_BYTES;
-            const int k = c * BK + lane;
-            const bool kin = k < p.K;
-#pragma unroll 8
+#pragma unroll
             for (int i = 0; i < 32; ++i) {
-                const int row = r0 + i;
-                const int gm = m0 + row;
-                float v = 0.f;
-                if (kin && gm < p.M) v = __ldg(p.A + (size_t)gm * p.lda + k);
-                const float hi = tf32_rna(v);
-                const float lo = tf32_rna(v - hi);
-                const int off = swz(row, lane);
+                const float hi = tf32_rna(v[i]);
+                const float lo = tf32_rna(v[i] - hi);
+                const int off = swz(r0 + i, lane);
                 *reinterpret_cast<float*>(a_hi + off) = hi;
                 *reinterpret_cast<float*>(a_lo + off) = lo;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA
             mbar_arrive(full_bar(s));
+            if (c + 1 < p.nchunks) load_chunk(c + 1);
         }
         // ===== epilogue: TMEM -> registers -> smem transpose -> coalesced global rows ==================================
         mbar_wait(tfull_bar, 0);
