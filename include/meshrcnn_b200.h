@@ -92,6 +92,12 @@ long long mrb_gemm_tc_image_bytes(int K, int N);
 int mrb_gemm_tc_pack(const float* src0, const float* src1, long long stride_k, long long stride_n, int split_axis,
                      int split_at, int K, int N, void* image, void* stream);
 int mrb_gemm_tc(const float* A, int lda, int M, int K, const void* image, int N, float* C, int ldc, void* stream);
+/* Weight gradients on the same tensor-core path: C[Kin x N] += X^T (V x Kin) * G (V x N), reduced over the V vertices
+ * (split over CTAs, fp32 vector reductions into C -- the caller zero-fills C).  Columns [0, n_split) go to C0 and
+ * [n_split, N) to C1 (both Kin x * with leading dimension ldc), so that dW0 and dW1 of a GraphConv come out of one
+ * pass over x and [gz | A^T gz].  N, n_split multiples of 32; C rows 16-byte aligned. */
+int mrb_gemm_tc_wgrad(const float* X, int ldx, const float* G, int ldg, int V, int Kin, int N, float* C0, float* C1,
+                      int n_split, int ldc, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * VertexAlign -- replaces VertexAlign.forward / single_projection / project, reference meshRCNN/layers.py:521-613,

@@ -321,6 +321,177 @@ static Plan make_plan(int K, int N) {
     return pl;
 }
 
+
+// ==========================================================================================================
+// Weight gradients:  C[Kin x N] += X^T[Kin x V] * G[V x N]   (reduction over the V vertices, split over CTAs)
+// ==========================================================================================================
+// In memory a vertex row of X / G is contiguous along M / N, i.e. the operands are "MN-major"; the producers transpose
+// them on the fly into the same K-major SWIZZLE_128B tiles the forward kernel uses: lane = one row (i or j) of a 32-row
+// block, four consecutive vertices form one 16-byte chunk -> one st.shared.v4 per (hi | lo), bank-conflict free because
+// the swizzle spreads the 8 rows of a quarter-warp over the 8 chunks of a 128-byte line.  Global loads stay coalesced
+// (a warp reads 32 consecutive floats of one vertex row).
+// grid = (M tiles, splits); each CTA reduces its slice of vertices into TMEM and adds the tile to C with fp32
+// reductions (C is zero-filled by the caller side of the C ABI).
+struct ParamsTN {
+    const float* X; int ldx;      // V x Kin
+    const float* G; int ldg;      // V x N
+    int V, Kin, N;                // N % 32 == 0, N <= 256
+    int chunks_per_split;
+    float* C0; float* C1;         // columns [0, n_split) -> C0 (ld ldc), [n_split, N) -> C1
+    int n_split, ldc;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) k_gemm_tn(ParamsTN p) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_base = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    const uint32_t tfull_bar = bar_base + 8u * (2 * STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i0 = blockIdx.x * BM;
+    const int NT = p.N;
+    const int b_bytes = NT * BK * 4;
+    const int total_chunks = (p.V + BK - 1) / BK;
+    const int c_beg = blockIdx.y * p.chunks_per_split;
+    const int c_end = min(total_chunks, c_beg + p.chunks_per_split);
+    const int nchunks = max(c_end - c_beg, 0);
+    int tmem_cols = 32;
+    while (tmem_cols < NT) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 128); mbar_init(empty_bar(s), 1); }
+        mbar_init(tfull_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp < 4) {
+        if (nchunks > 0) {
+            // ===== producers: warp w stages vertices [8w, 8w+8) of every chunk (= k-block w) ==========================
+            // warp w stages vertices [8w, 8w+8) of every chunk = 16-byte k-chunks 2w and 2w+1 of each tile row
+            float xa[32];            // [mb 0..3][kc 0..1][t 0..3]
+            float gb[64];            // [nb 0..7][kc 0..1][t 0..3]
+            auto load_chunk = [&](int c) {
+                const int v0 = c * BK + warp * 8;
+#pragma unroll
+                for (int kc = 0; kc < 2; ++kc)
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int v = v0 + kc * 4 + t;
+                        const bool vin = v < p.V;
+#pragma unroll
+                        for (int mb = 0; mb < 4; ++mb) {
+                            const int i = i0 + mb * 32 + lane;
+                            xa[(mb * 2 + kc) * 4 + t] = (vin && i < p.Kin) ? __ldg(p.X + (size_t)v * p.ldx + i) : 0.f;
+                        }
+#pragma unroll
+                        for (int nb = 0; nb < 8; ++nb) {
+                            const int j = nb * 32 + lane;
+                            gb[(nb * 2 + kc) * 4 + t] = (vin && j < NT) ? __ldg(p.G + (size_t)v * p.ldg + j) : 0.f;
+                        }
+                    }
+            };
+            auto split_store = [&](unsigned char* hi_t, unsigned char* lo_t, int row, int kchunk, const float* v) {
+                const int off = (row >> 3) * 1024 + (row & 7) * 128 + (((kchunk ^ (row & 7)) & 7) << 4);
+                float4 h, l;
+                h.x = tf32_rna(v[0]); h.y = tf32_rna(v[1]); h.z = tf32_rna(v[2]); h.w = tf32_rna(v[3]);
+                l.x = tf32_rna(v[0] - h.x); l.y = tf32_rna(v[1] - h.y); l.z = tf32_rna(v[2] - h.z); l.w = tf32_rna(v[3] - h.w);
+                *reinterpret_cast<float4*>(hi_t + off) = h;
+                *reinterpret_cast<float4*>(lo_t + off) = l;
+            };
+            load_chunk(c_beg);
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c & 1, use = c >> 1;
+                if (use > 0) mbar_wait(empty_bar(s), (use - 1) & 1);
+                unsigned char* a_hi = smem + s * STAGE_BYTES;
+                unsigned char* a_lo = a_hi + A_BYTES;
+                unsigned char* b_hi = a_hi + 2 * A_BYTES;
+                unsigned char* b_lo = b_hi + b_bytes;
+#pragma unroll
+                for (int kc = 0; kc < 2; ++kc) {
+#pragma unroll
+                    for (int mb = 0; mb < 4; ++mb)
+                        split_store(a_hi, a_lo, mb * 32 + lane, warp * 2 + kc, &xa[(mb * 2 + kc) * 4]);
+#pragma unroll
+                    for (int nb = 0; nb < 8; ++nb)
+                        if (nb * 32 < NT) split_store(b_hi, b_lo, nb * 32 + lane, warp * 2 + kc, &gb[(nb * 2 + kc) * 4]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(full_bar(s));
+                if (c + 1 < nchunks) load_chunk(c_beg + c + 1);
+            }
+            // ===== epilogue: TMEM -> registers -> vectorised fp32 reductions into C ========================================
+            mbar_wait(tfull_bar, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int i = i0 + warp * 32 + lane;       // TMEM lane = row of the tile
+            for (int c0 = 0; c0 < NT; c0 += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
+                      "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+                      "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (i < p.Kin) {
+                    float* dst = (c0 < p.n_split) ? p.C0 + (size_t)i * p.ldc + c0 : p.C1 + (size_t)i * p.ldc + (c0 - p.n_split);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                                     "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])),
+                                     "f"(__uint_as_float(v[j + 3]))
+                                     : "memory");
+                }
+            }
+        }
+    } else if (warp == 4) {
+        if (lane == 0 && nchunks > 0) {
+            const uint32_t idesc = umma_idesc(NT);
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c & 1, use = c >> 1;
+                mbar_wait(full_bar(s), use & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_BYTES;
+                const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + b_bytes;
+#pragma unroll
+                for (int kk = 0; kk < BK / 8; ++kk) {
+                    const uint64_t dah = umma_desc(a_hi + kk * 32), dal = umma_desc(a_lo + kk * 32);
+                    const uint64_t dbh = umma_desc(b_hi + kk * 32), dbl = umma_desc(b_lo + kk * 32);
+                    umma_tf32(tmem_d, dal, dbh, idesc, (c | kk) != 0);
+                    umma_tf32(tmem_d, dah, dbl, idesc, 1);
+                    umma_tf32(tmem_d, dah, dbh, idesc, 1);
+                }
+                umma_commit(empty_bar(s));
+            }
+            umma_commit(tfull_bar);
+        }
+        __syncwarp();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
+    }
+}
+
 }  // namespace gemmtc
 }  // namespace mrb
 
@@ -370,4 +541,34 @@ extern "C" int mrb_gemm_tc(const float* A, int lda, int M, int K, const void* im
     dim3 grid(ceil_div(M, BM), pl.ntiles);
     k_gemm_tc<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(p);
     return check_launch("gemm_tc");
+}
+
+extern "C" int mrb_gemm_tc_wgrad(const float* X, int ldx, const float* G, int ldg, int V, int Kin, int N, float* C0,
+                                 float* C1, int n_split, int ldc, void* stream_) {
+    MRB_REQUIRE(X && G && C0, "gemm_tc_wgrad: null pointer");
+    MRB_REQUIRE(N % 32 == 0 && N >= 32 && N <= NT_MAX, "gemm_tc_wgrad: N must be a multiple of 32 in [32, 256], got %d", N);
+    MRB_REQUIRE(n_split % 32 == 0 && n_split > 0 && n_split <= N && (n_split == N || C1), "gemm_tc_wgrad: bad column split");
+    MRB_REQUIRE(ldc % 4 == 0 && ((uintptr_t)C0 & 15) == 0 && (!C1 || ((uintptr_t)C1 & 15) == 0),
+                "gemm_tc_wgrad: C rows must be 16-byte aligned");
+    MRB_REQUIRE(Kin > 0 && V >= 0 && ldx >= Kin && ldg >= N, "gemm_tc_wgrad: bad shape");
+    if (V == 0) return MRB_OK;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_tn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) {
+            set_error("gemm_tc_wgrad: cannot reserve shared memory: %s", cudaGetErrorString(e));
+            return MRB_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    ParamsTN p;
+    p.X = X; p.ldx = ldx; p.G = G; p.ldg = ldg; p.V = V; p.Kin = Kin; p.N = N; p.C0 = C0; p.C1 = C1; p.n_split = n_split;
+    p.ldc = ldc;
+    const int mtiles = ceil_div(Kin, BM);
+    const int total_chunks = ceil_div(V, BK);
+    int splits = max(1, min(total_chunks, kNumSMs / mtiles));
+    p.chunks_per_split = ceil_div(total_chunks, splits);
+    splits = ceil_div(total_chunks, p.chunks_per_split);
+    k_gemm_tn<<<dim3(mtiles, splits), THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(p);
+    return check_launch("gemm_tc_wgrad");
 }

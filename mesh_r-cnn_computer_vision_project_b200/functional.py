@@ -129,6 +129,10 @@ def _use_tc(K: int, N: int) -> bool:
     return N >= 16 and K >= 16
 
 
+def _use_tc_wgrad(V: int, N: int) -> bool:
+    return N % 32 == 0 and 32 <= N <= 256 and V >= 256
+
+
 class _MatMul(torch.autograd.Function):
     """y = x @ (w^T if trans_w else w)."""
 
@@ -164,11 +168,16 @@ class _MatMul(torch.autograd.Function):
             else:
                 _gemm(False, not ctx.trans_w, M, K, N, _lib.ptr(gy), N, _lib.ptr(w), w.shape[1], 0.0, _lib.ptr(gx), K)
         if ctx.needs_input_grad[1]:
-            gw = torch.empty_like(w)
-            if ctx.trans_w:   # w: N x K ; gw = gy^T @ x
-                _gemm(True, False, N, K, M, _lib.ptr(gy), N, _lib.ptr(x), K, 0.0, _lib.ptr(gw), K)
-            else:             # w: K x N ; gw = x^T @ gy
-                _gemm(True, False, K, N, M, _lib.ptr(x), K, _lib.ptr(gy), N, 0.0, _lib.ptr(gw), N)
+            if _use_tc_wgrad(M, N):       # x^T @ gy (K x N) on the tensor cores; nn.Linear stores the transpose
+                gwt = torch.zeros(K, N, dtype=torch.float32, device=x.device)
+                _lib.call("mrb_gemm_tc_wgrad", _lib.ptr(x), K, _lib.ptr(gy), N, M, K, N, _lib.ptr(gwt), None, N, N)
+                gw = gwt.t().contiguous() if ctx.trans_w else gwt
+            else:
+                gw = torch.empty_like(w)
+                if ctx.trans_w:   # w: N x K ; gw = gy^T @ x
+                    _gemm(True, False, N, K, M, _lib.ptr(gy), N, _lib.ptr(x), K, 0.0, _lib.ptr(gw), K)
+                else:             # w: K x N ; gw = x^T @ gy
+                    _gemm(True, False, K, N, M, _lib.ptr(x), K, _lib.ptr(gy), N, 0.0, _lib.ptr(gw), N)
         return gx, gw, None
 
 
@@ -260,12 +269,18 @@ class _GraphConv(torch.autograd.Function):
             else:
                 _gemm(False, True, n, K, D, gp, 2 * D, _lib.ptr(w0), D, 0.0, _lib.ptr(gx), K)
                 _gemm(False, True, n, K, D, gp + 4 * D, 2 * D, _lib.ptr(w1), D, 1.0, _lib.ptr(gx), K)
-        if ctx.needs_input_grad[1]:
-            gw0 = torch.empty_like(w0)
-            _gemm(True, False, K, D, n, _lib.ptr(x), K, gp, 2 * D, 0.0, _lib.ptr(gw0), D)
-        if ctx.needs_input_grad[2]:
-            gw1 = torch.empty_like(w1)
-            _gemm(True, False, K, D, n, _lib.ptr(x), K, gp + 4 * D, 2 * D, 0.0, _lib.ptr(gw1), D)
+        if (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) and _use_tc_wgrad(n, 2 * D) and D % 32 == 0:
+            # dW0 | dW1 = x^T @ [gz | A^T gz]: one tensor-core pass over x and gy, reduced over the vertices
+            gw = torch.zeros(2, K, D, dtype=torch.float32, device=x.device)
+            _lib.call("mrb_gemm_tc_wgrad", _lib.ptr(x), K, gp, 2 * D, n, K, 2 * D, _lib.ptr(gw), _lib.ptr(gw) + 4 * K * D, D, D)
+            gw0, gw1 = gw[0], gw[1]
+        else:
+            if ctx.needs_input_grad[1]:
+                gw0 = torch.empty_like(w0)
+                _gemm(True, False, K, D, n, _lib.ptr(x), K, gp, 2 * D, 0.0, _lib.ptr(gw0), D)
+            if ctx.needs_input_grad[2]:
+                gw1 = torch.empty_like(w1)
+                _gemm(True, False, K, D, n, _lib.ptr(x), K, gp + 4 * D, 2 * D, 0.0, _lib.ptr(gw1), D)
         return gx, gw0, gw1, None
 
 

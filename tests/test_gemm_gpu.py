@@ -56,3 +56,21 @@ def test_tc_gemm_split_sources(lib):
     _check(513, 131, 256, split="n")                   # GraphConv forward  x @ [W0 | W1]
     _check(513, 256, 131, split="k")                   # GraphConv backward gy @ [W0 | W1]^T
     _check(513, 256, 387, split="k")
+
+
+@pytest.mark.parametrize("V,Kin,N,split", [(1000, 128, 256, 128), (4097, 131, 256, 128), (50353, 387, 256, 128),
+                                           (333, 259, 128, 128), (70, 16, 32, 32), (5000, 3840, 128, 128)])
+def test_tc_wgrad(lib, V, Kin, N, split):
+    """C0 | C1 = X^T @ G on the tensor cores (MN-major operands, split over CTAs, fp32 reductions)."""
+    from meshrcnn_b200 import _lib
+    g = torch.Generator().manual_seed(V + Kin)
+    x, gy = torch.randn(V, Kin, generator=g), torch.randn(V, N, generator=g)
+    xd, gd = x.cuda(), gy.cuda()
+    c0 = torch.zeros(Kin, split, device="cuda")
+    c1 = torch.zeros(Kin, N - split, device="cuda") if split < N else None
+    _lib.call("mrb_gemm_tc_wgrad", _lib.ptr(xd), Kin, _lib.ptr(gd), N, V, Kin, N, _lib.ptr(c0), _lib.ptr(c1), split, split)
+    torch.cuda.synchronize()
+    want = x.double().t() @ gy.double()
+    got = torch.cat([c0, c1], 1) if c1 is not None else c0
+    err = float((got.cpu().double() - want).abs().max())
+    assert err <= 1e-5 * float(want.abs().max()), (V, Kin, N, err, float(want.abs().max()))
