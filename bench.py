@@ -15,10 +15,10 @@ One JSON line on stdout (rank 0).  `value` = steps with inputs resident in HBM; 
 module API with inputs in pinned host memory, H2D + D2H inside the timed region.
 """
 import argparse
+import gc
 import json
 import os
 import sys
-import threading
 import time
 
 import torch
@@ -41,48 +41,53 @@ def log(*a):
 # ---------------------------------------------------------------------------------------------------------------
 # clocks
 # ---------------------------------------------------------------------------------------------------------------
-class ClockSampler(threading.Thread):
-    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+class ClockSampler:
+    """Samples SM clock + throttle reasons with a background `nvidia-smi -lms 200` process while the timed regions run
+    (a separate process: NVML calls made from inside the benchmark process were seen to stall kernel launches)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
-        self._stop_evt = threading.Event()
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-        except Exception as e:     # noqa: BLE001
-            self.nv = None
-            log("[bench] NVML unavailable:", e)
+        self.index, self.proc, self.path = index, None, "/tmp/mrb_clocks_%d.csv" % os.getpid()
 
-    def run(self):
-        if self.nv is None:
+    def start(self):
+        import shutil
+        import subprocess
+        exe = shutil.which("nvidia-smi")
+        if exe is None:
+            log("[bench] nvidia-smi not found: no clock samples")
             return
-        nv = self.nv
-        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
-                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
-                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
-                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
-        while not self._stop_evt.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for k, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(k)
-            except Exception:      # noqa: BLE001
-                pass
-            self._stop_evt.wait(0.05)
+        self.out = open(self.path, "w")
+        self.proc = subprocess.Popen([exe, "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                                      "-lms", "200"], stdout=self.out, stderr=subprocess.DEVNULL)
 
     def stop(self):
-        self._stop_evt.set()
-        self.join(timeout=2)
-        s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:      # noqa: BLE001
+            self.proc.kill()
+        self.out.close()
+        mhz, mx, reasons = [], None, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6 or not f[0].isdigit():
+                continue
+            mhz.append(int(f[0]))
+            mx = int(f[1]) if f[1].isdigit() else mx
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        mhz.sort()
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(mhz)}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -147,12 +152,13 @@ def run_cuda(args):
     gv, gvi, gfaces, gfi, _ = Cubify(0.5)(gt_vox_h.to(dev))
     gt = MeshTargets(torch.cat([normalize_mesh(v) for v in gv.split(gvi)]), gfaces, gvi, gfi)
 
-    def step(vox_d, fmap_d):
+    def step(vox_d, fmap_d, exchange=True):
         bucket.zero()
         fmap_d.grad = None
         losses = head(vox_d, fmap_d, sizes, gt)
         weighted_loss(losses).backward()
-        bucket.all_reduce()
+        if exchange:
+            bucket.all_reduce()          # the step's one collective: NCCL all-reduce(SUM) of the flat gradient bucket
         return losses
 
     vox_d = vox_h.to(dev)
@@ -175,6 +181,8 @@ def run_cuda(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
+    gc.collect()
+    gc.disable()            # no cyclic-GC pause inside a timed step (autograd graphs are freed by refcount)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     sync_all()
     l0 = _lib.launch_count
@@ -186,20 +194,30 @@ def run_cuda(args):
     sync_all()
     launches = (_lib.launch_count - l0) // args.steps
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    log('[bench] per-step ms (resident):', ' '.join('%.2f' % a.elapsed_time(b) for a, b in ev))
     # ---- timed region 2: end to end through the module API from pinned host memory --------------------------------
     ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     host_losses = None
     sync_all()
+    host_phase = []
     for a, b in ev2:
         flush.zero_()
         a.record()
+        t0 = time.perf_counter()
         v = vox_pin.to(dev, non_blocking=True)
         f = fmap_pin.to(dev, non_blocking=True).requires_grad_()
+        t1 = time.perf_counter()
         losses = step(v, f)
-        host_losses = torch.stack([losses["chamfer_loss"], losses["normal_loss"], losses["edge_loss"]]).cpu()   # D2H
+        t2 = time.perf_counter()
+        host_losses = torch.stack([losses["chamfer_loss"], losses["normal_loss"], losses["edge_loss"]]).detach().cpu()   # D2H
+        t3 = time.perf_counter()
         b.record()
+        host_phase.append((t1 - t0, t2 - t1, t3 - t2))
+    log("[bench] e2e host phases ms (h2d, step, d2h):", " ".join("%.1f/%.1f/%.1f" % (x * 1e3, y * 1e3, z * 1e3) for x, y, z in host_phase))
     sync_all()
     e2e_ms = sum(a.elapsed_time(b) for a, b in ev2)
+    gc.enable()
+    log('[bench] per-step ms (e2e):', ' '.join('%.2f' % a.elapsed_time(b) for a, b in ev2))
     clocks = sampler.stop() if sampler else None
 
     t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
@@ -212,7 +230,7 @@ def run_cuda(args):
     if rank == 0:
         with _lib.timed_calls() as tc:
             for _ in range(2):
-                step(vox_d, fmap_d)
+                step(vox_d, fmap_d, exchange=False)      # rank-local: the other ranks are not in this region
         breakdown = {k: {"ms_per_step": round(v / 2, 4), "calls_per_step": tc.calls[k] // 2} for k, v in
                      sorted(tc.ms.items(), key=lambda kv: -kv[1])}
         peaks = {"hbm_gbs": 6650.0, "src": "fallback"}
@@ -234,6 +252,17 @@ def run_cuda(args):
             a = work["gather_bytes_per_launch"] / per / 1e9
             roof_all["mrb_csr_gather_fwd"] = {"bound": "hbm", "achieved": round(a, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                               "frac": round(a / peaks["hbm_gbs"], 4)}
+        if "mrb_gemm_tc" in breakdown:
+            # forward + input-gradient projections: per stage K in {259|387, 131, 131} -> N = 256 and back
+            ms = breakdown["mrb_gemm_tc"]["ms_per_step"] * 1e-3
+            SVn = stats["SV"]
+            ks = [259, 131, 131, 387, 131, 131, 387, 131, 131]
+            flops = sum(2.0 * SVn * k * 256 for k in ks) * 2                     # fwd + dgrad
+            byts = sum(4.0 * SVn * (k + 256) for k in ks) * 2                    # A read + C written once
+            roof_all["mrb_gemm_tc"] = {"bound": "hbm (intensity < ridge at N<=256)", "achieved": round(byts / ms / 1e9, 1),
+                                       "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(byts / ms / 1e9 / peaks["hbm_gbs"], 4),
+                                       "tensor_tflops_fp32_equiv": round(flops / ms / 1e12, 1),
+                                       "tensor_tflops_tf32_issued": round(3 * flops / ms / 1e12, 1)}
         if "mrb_cubify_emit" in breakdown:
             per = (breakdown["mrb_cubify_emit"]["ms_per_step"] + breakdown["mrb_cubify_count"]["ms_per_step"]) * 1e-3
             a = work["cubify_bytes"] / per / 1e9
@@ -277,7 +306,7 @@ def run_cuda(args):
         dist.barrier()
         dist.destroy_process_group()
     if result is not None:
-        print(json.dumps(result), flush=True)
+        emit(result)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -352,7 +381,16 @@ def run_reference(args):
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "meshes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def emit(line: dict) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+# Everything except the result line goes to stderr: libraries (NCCL prints its version banner) write to fd 1.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():

@@ -1,2 +1,2 @@
-timeout 600 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
-timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench5.json 2> gpurun_out/bench5.err; echo rc=$?
+timeout 240 python bench.py --steps 30 --warmup 3 --no-cpu-baseline > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err; echo rc=$?
+grep -E "per-step|phases" gpurun_out/bench_1gpu.err | cut -c1-700
