@@ -1,2 +1,2 @@
-timeout 240 python bench.py --steps 30 --warmup 3 --no-cpu-baseline > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err; echo rc=$?
-grep -E "per-step|phases" gpurun_out/bench_1gpu.err | cut -c1-700
+timeout 200 python -m pytest tests/test_cubify_gpu.py -x -q -m gpu 2>&1 | tail -3
+timeout 100 python scripts/cubify_stress.py

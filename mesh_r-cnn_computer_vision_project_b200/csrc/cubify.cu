@@ -228,33 +228,52 @@ __global__ void __launch_bounds__(CH) k_emit_verts(Dims d, Workspace ws, float* 
     }
 }
 
-// pass 2b: adjacency, one thread per vertex, neighbours in ascending lattice order (== ascending vertex id)
-__global__ void __launch_bounds__(256) k_emit_adj(Dims d, Workspace ws, int SV, const int32_t* __restrict__ rowptr,
-                                                  const uint32_t* __restrict__ vmask, const int32_t* __restrict__ vlat,
-                                                  long long* __restrict__ adj_row, long long* __restrict__ adj_col,
-                                                  int32_t* __restrict__ col32) {
-    const int vid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (vid >= SV) return;
-    uint32_t m = vmask[vid];
-    const int lat = vlat[vid];
-    int e = rowptr[vid];
-    const int sY = d.LX, sZ = d.LX * d.LY;
-    while (m) {
-        const int bit = __ffs(m) - 1;
-        m &= m - 1;
-        const int dz = bit / 9 - 1, dy = (bit / 3) % 3 - 1, dx = bit % 3 - 1;
-        const int c = ws.rank[lat + dz * sZ + dy * sY + dx];
-        adj_row[e] = vid;
-        adj_col[e] = c;
-        col32[e] = c;
-        ++e;
+// pass 2b: adjacency.  One thread per vertex enumerates its neighbours in ascending lattice order (== ascending
+// vertex id); the block's edges form one contiguous output range, so they are staged in shared memory and streamed out
+// with fully coalesced int64 / int32 stores (the 16 B/edge COO + 4 B/edge CSR streams are the bulk of Cubify's traffic).
+constexpr int ADJ_BLOCK = 256;
+constexpr int ADJ_CAP = ADJ_BLOCK * 18;   // a lattice vertex has at most 18 neighbours (6 axis + 12 face-diagonal)
+
+__global__ void __launch_bounds__(ADJ_BLOCK) k_emit_adj(Dims d, Workspace ws, int SV, const int32_t* __restrict__ rowptr,
+                                                        const uint32_t* __restrict__ vmask, const int32_t* __restrict__ vlat,
+                                                        long long* __restrict__ adj_row, long long* __restrict__ adj_col,
+                                                        int32_t* __restrict__ col32) {
+    __shared__ int32_t s_col[ADJ_CAP];
+    __shared__ unsigned char s_row[ADJ_CAP];
+    const int v0 = blockIdx.x * ADJ_BLOCK;
+    const int vid = v0 + threadIdx.x;
+    const int e_begin = rowptr[v0];
+    const int e_end = rowptr[min(v0 + ADJ_BLOCK, SV)];
+    if (vid < SV) {
+        uint32_t m = vmask[vid];
+        const int lat = vlat[vid];
+        int e = rowptr[vid] - e_begin;
+        const int sY = d.LX, sZ = d.LX * d.LY;
+        while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            const int dz = bit / 9 - 1, dy = (bit / 3) % 3 - 1, dx = bit % 3 - 1;
+            s_col[e] = ws.rank[lat + dz * sZ + dy * sY + dx];
+            s_row[e] = (unsigned char)threadIdx.x;
+            ++e;
+        }
+    }
+    __syncthreads();
+    const int n = e_end - e_begin;
+    for (int e = threadIdx.x; e < n; e += ADJ_BLOCK) {
+        const int c = s_col[e];
+        adj_row[(size_t)e_begin + e] = v0 + s_row[e];
+        adj_col[(size_t)e_begin + e] = c;
+        col32[(size_t)e_begin + e] = c;
     }
 }
 
-// pass 2c: faces in (b, dir, z, y, x) order, two triangles (c0,c1,c2),(c0,c2,c3) per quad, per-mesh local ids
+// pass 2c: faces in (b, dir, z, y, x) order, two triangles (c0,c1,c2),(c0,c2,c3) per quad, per-mesh local ids.
+// Per direction the block's quads are one contiguous output range: staged in shared memory, written coalesced.
 __global__ void __launch_bounds__(CH) k_emit_faces(Dims d, Workspace ws, const long long* __restrict__ meta,
                                                    long long* __restrict__ faces) {
     __shared__ int wtot[6][CH / 32];
+    __shared__ int32_t stage[CH * 6];
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int v = chunk * CH + threadIdx.x;
     const unsigned f = (v < d.nvox) ? ws.ff[(size_t)b * d.nvox + v] : 0u;
@@ -266,26 +285,33 @@ __global__ void __launch_bounds__(CH) k_emit_faces(Dims d, Workspace ws, const l
         if (lane_id() == 0) wtot[k][warp_id()] = __popc(bal);
     }
     __syncthreads();
-    if (!f) return;
     const int x = v % d.X, y = (v / d.X) % d.Y, z = v / (d.X * d.Y);
     const int voff = (int)meta[4 + 2 * d.B + b];
     const int32_t* rk = ws.rank + (size_t)b * d.nlat;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-        if (!((f >> k) & 1u)) continue;
-        int pos = pre[k];
-        for (int w = 0; w < warp_id(); ++w) pos += wtot[k][w];
-        const long long q = (long long)ws.faceOff[((size_t)b * 6 + k) * d.nchF + chunk] + pos;
-        long long c[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int lz = z + kCorner[k][j][0], ly = y + kCorner[k][j][1], lx = x + kCorner[k][j][2];
-            c[j] = rk[((size_t)lz * d.LY + ly) * d.LX + lx] - voff;
+        int total = 0, before = 0;
+        for (int w = 0; w < CH / 32; ++w) {
+            const int t = wtot[k][w];
+            before += (w < warp_id()) ? t : 0;
+            total += t;
         }
-        longlong2* out = reinterpret_cast<longlong2*>(faces + q * 6);
-        out[0] = make_longlong2(c[0], c[1]);
-        out[1] = make_longlong2(c[2], c[0]);
-        out[2] = make_longlong2(c[2], c[3]);
+        if (total == 0) continue;                 // block-uniform
+        if ((f >> k) & 1u) {
+            int c[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int lz = z + kCorner[k][j][0], ly = y + kCorner[k][j][1], lx = x + kCorner[k][j][2];
+                c[j] = rk[((size_t)lz * d.LY + ly) * d.LX + lx] - voff;
+            }
+            int32_t* o = stage + (before + pre[k]) * 6;
+            o[0] = c[0]; o[1] = c[1]; o[2] = c[2]; o[3] = c[0]; o[4] = c[2]; o[5] = c[3];
+        }
+        __syncthreads();
+        const long long q0 = ws.faceOff[((size_t)b * 6 + k) * d.nchF + chunk];
+        long long* out = faces + q0 * 6;
+        for (int t = threadIdx.x; t < total * 6; t += CH) out[t] = stage[t];
+        __syncthreads();
     }
 }
 
@@ -330,7 +356,7 @@ extern "C" int mrb_cubify_emit(int B, int Z, int Y, int X, void* workspace, cons
     uint32_t* vmask = (uint32_t*)vert_aux;
     int32_t* vlat = (int32_t*)vert_aux + SV;
     k_emit_verts<<<dim3(d.nchL, B), CH, 0, stream>>>(d, ws, verts, rowptr, vert_mesh, vmask, vlat);
-    k_emit_adj<<<ceil_div(SV, 256), 256, 0, stream>>>(d, ws, (int)SV, rowptr, vmask, vlat, adj, adj + E, col32);
+    k_emit_adj<<<ceil_div(SV, ADJ_BLOCK), ADJ_BLOCK, 0, stream>>>(d, ws, (int)SV, rowptr, vmask, vlat, adj, adj + E, col32);
     k_emit_faces<<<dim3(d.nchF, B), CH, 0, stream>>>(d, ws, meta, faces);
     return check_launch("cubify_emit");
 }
