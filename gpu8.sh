@@ -1,2 +1,2 @@
-timeout 200 python -m pytest tests/test_cubify_gpu.py -x -q -m gpu 2>&1 | tail -3
-timeout 100 python scripts/cubify_stress.py
+timeout 300 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/bench7.json 2> gpurun_out/bench7.err; echo rc=$?

@@ -10,12 +10,15 @@
 // Arithmetic intensity at N <= 256 is below the B200 ridge, so the kernel is HBM-bound by design: A is read once,
 // C written once, and the weight image (<= 0.8 MB) streams from L2.
 //
-// CTA = one 128-row M tile x one N tile (<= 256 columns).  Warp roles (192 threads):
-//   warps 0-3  producers: coalesced fp32 loads of the A chunk (128 x 32), hi/lo split, swizzled st.shared,
-//              fence.proxy.async, mbarrier arrive;   afterwards the epilogue: tcgen05.ld -> smem transpose -> coalesced C
-//   warp 4     lane 0 issues tcgen05.mma (kind::tf32, M=128, N=NT, K=8), tcgen05.commit frees the stage / signals the epilogue;
-//              the whole warp owns the TMEM allocation
-//   warp 5     lane 0 streams the packed weight chunk with cp.async.bulk (TMA bulk copy) onto the stage's mbarrier
+// Persistent CTAs (one per SM) loop over 128-row M tiles x N tiles (<= 256 columns).  Warp roles (576 threads):
+//   warps 0-7   A producers: coalesced fp32 loads of the A chunk (128 x 32), 2 chunks in flight per thread, hi/lo split,
+//               swizzled st.shared, fence.proxy.async, mbarrier arrive
+//   warps 8-15  epilogue: tcgen05.ld (TMEM lane quadrant = warp % 4, column half = warp / 12) -> st.global.v4 for aligned C
+//               rows, shared-memory transpose otherwise; the TMEM accumulator is double buffered, so tile j's write-back
+//               overlaps tile j+1's MMAs
+//   warp 16     lane 0 issues tcgen05.mma (kind::tf32, M=128, N=NT, K=8), tcgen05.commit frees the stage / signals the
+//               epilogue; the whole warp owns the TMEM allocation
+//   warp 17     lane 0 streams the packed weight chunk with cp.async.bulk (TMA bulk copy) onto the stage's mbarrier
 #include "common.cuh"
 #include "../../include/meshrcnn_b200.h"
 
@@ -97,163 +100,240 @@ struct Params {
     const unsigned char* image;   // [n_tile][chunk][hi|lo][NT rows][128 B]
     int N, NT, nchunks, tmem_cols;   // tmem_cols: columns of one accumulator
     int nacc;                        // accumulators used round-robin over the K chunks (bounds the fp32 chain length)
+    int acc_bufs;                    // 2: the epilogue of tile j overlaps the MMAs of tile j+1 (double-buffered TMEM)
+    int mtiles, ntiles;
     float* C;
     int ldc;
 };
 
-__global__ void __launch_bounds__(THREADS, 1) k_gemm_tc(Params p) {
+constexpr int PROD_WARPS = 8;        // A producer warps, 16 rows of the 128-row tile each
+constexpr int PROD_ROWS = BM / PROD_WARPS;
+constexpr int PREFETCH = 2;          // A chunks in flight per producer thread (registers)
+constexpr int EPI_WARPS = 8;         // epilogue warps: TMEM lane quadrant = warp % 4, column half = (warp - PROD_WARPS) / 4
+constexpr int TC_THREADS = (PROD_WARPS + EPI_WARPS + 2) * 32;   // producers | epilogue warps | MMA issuer | weight TMA
+constexpr int EPI_BYTES = EPI_WARPS * 32 * 33 * 4;
+constexpr int TC_SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
+
+// Persistent: grid = min(#tiles, #SMs); every role loops over the CTA's tiles with pipeline state that carries across
+// tiles, so global-load latency, tensor work and the C write-back of consecutive tiles overlap on one SM.
+__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);   // full[2], empty[2], tmem_full
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    float* epi = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);   // full[2] empty[2] tfull[2] tempty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-    const uint32_t tfull_bar = bar_base + 8u * (2 * STAGES);
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM;
-    const int ntile = blockIdx.y;
     const int NT = p.NT;
     const int b_bytes = NT * BK * 4;     // one (hi | lo) weight tile
+    const int total_tiles = p.mtiles * p.ntiles;
+    const int my_tiles = (total_tiles > (int)blockIdx.x) ? (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int acc_cols = p.tmem_cols * p.nacc;
+    const int tmem_total = acc_cols * p.acc_bufs;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full_bar(s), 128 + 1);
+            mbar_init(full_bar(s), PROD_WARPS * 32 + 1);
             mbar_init(empty_bar(s), 1);
         }
-        mbar_init(tfull_bar, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), EPI_WARPS * 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == PROD_WARPS + EPI_WARPS) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(p.tmem_cols * p.nacc)
+                     "r"(tmem_total)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_d = *tmem_slot;
+    const uint32_t tmem_base = *tmem_slot;
 
-    if (warp < 4) {
+    if (warp < PROD_WARPS) {
         // ===== A producers ======================================================================================
-        const int r0 = warp * 32;
-        // All 32 row segments of the next chunk are requested before the current one is converted, so every producer
-        // thread keeps 32 independent 128-byte-coalesced loads in flight across the stage hand-over (the loop is
-        // load-latency bound otherwise: the MMA needs ~0.8 us per chunk, an L2/HBM round trip takes about as long).
-        float v[32];
-        auto load_chunk = [&](int c) {
+        // The kernel is bound by global-load latency unless enough bytes are in flight, so every producer thread keeps
+        // PREFETCH chunks (16 coalesced 128-byte row segments each) outstanding in registers, across tile boundaries.
+        const int r0 = warp * PROD_ROWS;
+        const int total_its = my_tiles * p.nchunks;
+        float v[PREFETCH][PROD_ROWS];
+        auto load_it = [&](int it, float (&dst)[PROD_ROWS]) {
+            const int tile = blockIdx.x + (it / p.nchunks) * gridDim.x;
+            const int c = it % p.nchunks;
+            const int m0 = (tile / p.ntiles) * BM;
             const int k = c * BK + lane;
             const bool kin = k < p.K;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
+            for (int i = 0; i < PROD_ROWS; ++i) {
                 const int gm = m0 + r0 + i;
-                v[i] = (kin && gm < p.M) ? __ldg(p.A + (size_t)gm * p.lda + k) : 0.f;
+                dst[i] = (kin && gm < p.M) ? __ldg(p.A + (size_t)gm * p.lda + k) : 0.f;
             }
         };
-        load_chunk(0);
-        for (int c = 0; c < p.nchunks; ++c) {
-            const int s = c & 1, use = c >> 1;
-            if (use > 0) mbar_wait(empty_bar(s), (use - 1) & 1);
-            unsigned char* a_hi = smem + s * STAGE_BYTES;
-            unsigned char* a_lo = a_hi + A_BYTES;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const float hi = tf32_rna(v[i]);
-                const float lo = tf32_rna(v[i] - hi);
-                const int off = swz(r0 + i, lane);
-                *reinterpret_cast<float*>(a_hi + off) = hi;
-                *reinterpret_cast<float*>(a_lo + off) = lo;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA
-            mbar_arrive(full_bar(s));
-            if (c + 1 < p.nchunks) load_chunk(c + 1);
-        }
-        // ===== epilogue: TMEM -> registers -> smem transpose -> coalesced global rows ==================================
-        mbar_wait(tfull_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        float* stage_t = reinterpret_cast<float*>(smem) + warp * (32 * 33);   // stage buffers are free now
-        const int n0 = ntile * NT;
-        for (int c0 = 0; c0 < NT; c0 += 32) {
-            float acc[32];
+        for (int d = 0; d < PREFETCH; ++d)
+            if (d < total_its) load_it(d, v[d]);
+        for (int it0 = 0; it0 < total_its; it0 += PREFETCH) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-            for (int a = 0; a < p.nacc; ++a) {
-                uint32_t v[32];
-                const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * p.tmem_cols + c0);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
-                      "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
-                      "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (int d = 0; d < PREFETCH; ++d) {
+                const int it = it0 + d;
+                if (it < total_its) {
+                    const int s = it % STAGES, use = it / STAGES;
+                    if (use > 0) mbar_wait(empty_bar(s), (use - 1) & 1);
+                    unsigned char* a_hi = smem + s * STAGE_BYTES;
+                    unsigned char* a_lo = a_hi + A_BYTES;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(v[j]);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) stage_t[lane * 33 + j] = acc[j];
-            __syncwarp();
-            const int col = n0 + c0 + lane;
-            if (c0 + lane < NT && col < p.N) {
-#pragma unroll 4
-                for (int r = 0; r < 32; ++r) {
-                    const int gm = m0 + warp * 32 + r;
-                    if (gm < p.M) p.C[(size_t)gm * p.ldc + col] = stage_t[r * 33 + lane];
+                    for (int i = 0; i < PROD_ROWS; ++i) {
+                        const float hi = tf32_rna(v[d][i]);
+                        const float lo = tf32_rna(v[d][i] - hi);
+                        const int off = swz(r0 + i, lane);
+                        *reinterpret_cast<float*>(a_hi + off) = hi;
+                        *reinterpret_cast<float*>(a_lo + off) = lo;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA
+                    mbar_arrive(full_bar(s));
+                    if (it + PREFETCH < total_its) load_it(it + PREFETCH, v[d]);
                 }
             }
-            __syncwarp();
         }
-    } else if (warp == 4) {
+    } else if (warp < PROD_WARPS + EPI_WARPS) {
+        // ===== epilogue: TMEM -> registers -> C =========================================================================
+        // Warp w reads TMEM lane quadrant w % 4 (= 32 rows of the tile) and the column blocks of its half.  16-byte aligned
+        // C rows are written straight from registers (each thread owns 32 consecutive columns of one row -> 8 x st.v4);
+        // otherwise the block is transposed through shared memory so that every store instruction covers one 128-byte row
+        // segment.
+        const int ew = warp & 3;                       // TMEM lane quadrant (PROD_WARPS is a multiple of 4)
+        const int half = (warp - PROD_WARPS) >> 2;     // 0 | 1
+        float* stage_t = epi + (warp - PROD_WARPS) * (32 * 33);
+        const bool aligned = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+        const int nblk = (NT + 31) / 32;
+        const int blk_beg = half * ((nblk + 1) / 2), blk_end = half ? nblk : (nblk + 1) / 2;
+        int j = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+            const int ab = j % p.acc_bufs, use = j / p.acc_bufs;
+            const int m0 = (tile / p.ntiles) * BM, n0 = (tile % p.ntiles) * NT;
+            mbar_wait(tfull_bar(ab), use & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_d = tmem_base + (uint32_t)(ab * acc_cols);
+            const int gm_mine = m0 + ew * 32 + lane;
+            for (int blk = blk_beg; blk < blk_end; ++blk) {
+                const int c0 = blk * 32;
+                float acc[32];
+#pragma unroll
+                for (int q = 0; q < 32; ++q) acc[q] = 0.f;
+                for (int a = 0; a < p.nacc; ++a) {
+                    uint32_t v[32];
+                    const uint32_t taddr = tmem_d + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * p.tmem_cols + c0);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
+                          "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+                          "=r"(v[30]), "=r"(v[31])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) acc[q] += __uint_as_float(v[q]);
+                }
+                if (blk + 1 == blk_end) {
+                    // last read of this accumulator by this warp: hand the TMEM buffer back before the stores
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(tempty_bar(ab));
+                }
+                const int colbase = n0 + c0;
+                if (aligned && c0 + 32 <= NT && colbase + 32 <= p.N) {
+                    if (gm_mine < p.M) {
+                        float4* dst = reinterpret_cast<float4*>(p.C + (size_t)gm_mine * p.ldc + colbase);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) dst[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+                    }
+                } else {
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) stage_t[lane * 33 + q] = acc[q];
+                    __syncwarp();
+                    const int col = colbase + lane;
+                    if (c0 + lane < NT && col < p.N) {
+                        float* dst = p.C + (size_t)(m0 + ew * 32) * p.ldc + col;
+                        const int rmax = min(32, p.M - (m0 + ew * 32));
+#pragma unroll 8
+                        for (int r = 0; r < 32; ++r)
+                            if (r < rmax) dst[(size_t)r * p.ldc] = stage_t[r * 33 + lane];
+                    }
+                    __syncwarp();
+                }
+            }
+            if (blk_beg >= blk_end) {                 // this half has no column block (NT <= 32): still release the buffer
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(tempty_bar(ab));
+            }
+        }
+    } else if (warp == PROD_WARPS + EPI_WARPS) {
         // ===== MMA issuer ========================================================================================
         if (lane == 0) {
             const uint32_t idesc = umma_idesc(NT);
-            for (int c = 0; c < p.nchunks; ++c) {
-                const int s = c & 1, use = c >> 1;
-                mbar_wait(full_bar(s), use & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_BYTES;
-                const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + b_bytes;
-#pragma unroll
-                for (int kk = 0; kk < BK / 8; ++kk) {
-                    const uint64_t dah = umma_desc(a_hi + kk * 32), dal = umma_desc(a_lo + kk * 32);
-                    const uint64_t dbh = umma_desc(b_hi + kk * 32), dbl = umma_desc(b_lo + kk * 32);
-                    const uint32_t d = tmem_d + (uint32_t)((c % p.nacc) * p.tmem_cols);
-                    umma_tf32(d, dal, dbh, idesc, (c >= p.nacc) || kk != 0);
-                    umma_tf32(d, dah, dbl, idesc, 1);
-                    umma_tf32(d, dah, dbh, idesc, 1);
+            int it = 0, j = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+                const int ab = j % p.acc_bufs, use = j / p.acc_bufs;
+                if (use > 0) {
+                    mbar_wait(tempty_bar(ab), (use - 1) & 1);          // epilogue has drained this accumulator
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
-                umma_commit(empty_bar(s));                 // stage reusable once these MMAs retire
+                const uint32_t tmem_d = tmem_base + (uint32_t)(ab * acc_cols);
+                for (int c = 0; c < p.nchunks; ++c, ++it) {
+                    const int s = it % STAGES, suse = it / STAGES;
+                    mbar_wait(full_bar(s), suse & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_BYTES;
+                    const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + b_bytes;
+#pragma unroll
+                    for (int kk = 0; kk < BK / 8; ++kk) {
+                        const uint64_t dah = umma_desc(a_hi + kk * 32), dal = umma_desc(a_lo + kk * 32);
+                        const uint64_t dbh = umma_desc(b_hi + kk * 32), dbl = umma_desc(b_lo + kk * 32);
+                        const uint32_t d = tmem_d + (uint32_t)((c % p.nacc) * p.tmem_cols);
+                        umma_tf32(d, dal, dbh, idesc, (c >= p.nacc) || kk != 0);
+                        umma_tf32(d, dah, dbl, idesc, 1);
+                        umma_tf32(d, dah, dbh, idesc, 1);
+                    }
+                    umma_commit(empty_bar(s));                 // stage reusable once these MMAs retire
+                }
+                umma_commit(tfull_bar(ab));                    // accumulator complete -> epilogue
             }
-            umma_commit(tfull_bar);                        // accumulator complete -> epilogue
         }
         __syncwarp();
     } else {
         // ===== weight-chunk TMA (bulk copy) producer =======================================================================
         if (lane == 0) {
-            const unsigned char* img = p.image + (size_t)ntile * p.nchunks * 2 * b_bytes;
-            for (int c = 0; c < p.nchunks; ++c) {
-                const int s = c & 1, use = c >> 1;
-                if (use > 0) mbar_wait(empty_bar(s), (use - 1) & 1);
-                const uint32_t dst = smem_base + s * STAGE_BYTES + 2 * A_BYTES;
-                mbar_expect_tx(full_bar(s), 2 * b_bytes);
-                bulk_g2s(dst, img + (size_t)c * 2 * b_bytes, b_bytes, full_bar(s));
-                bulk_g2s(dst + b_bytes, img + (size_t)c * 2 * b_bytes + b_bytes, b_bytes, full_bar(s));
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const unsigned char* img = p.image + (size_t)(tile % p.ntiles) * p.nchunks * 2 * b_bytes;
+                for (int c = 0; c < p.nchunks; ++c, ++it) {
+                    const int s = it % STAGES, use = it / STAGES;
+                    if (use > 0) mbar_wait(empty_bar(s), (use - 1) & 1);
+                    const uint32_t dst = smem_base + s * STAGE_BYTES + 2 * A_BYTES;
+                    mbar_expect_tx(full_bar(s), 2 * b_bytes);
+                    bulk_g2s(dst, img + (size_t)c * 2 * b_bytes, b_bytes, full_bar(s));
+                    bulk_g2s(dst + b_bytes, img + (size_t)c * 2 * b_bytes + b_bytes, b_bytes, full_bar(s));
+                }
             }
         }
         __syncwarp();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 4) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(p.tmem_cols * p.nacc) : "memory");
+    if (warp == PROD_WARPS + EPI_WARPS) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_total) : "memory");
     }
 }
 
@@ -527,9 +607,9 @@ extern "C" int mrb_gemm_tc(const float* A, int lda, int M, int K, const void* im
     if (M == 0) return MRB_OK;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
         if (e != cudaSuccess) {
-            set_error("gemm_tc: cannot reserve %d bytes of shared memory: %s", SMEM_BYTES, cudaGetErrorString(e));
+            set_error("gemm_tc: cannot reserve %d bytes of shared memory: %s", TC_SMEM_BYTES, cudaGetErrorString(e));
             return MRB_ERR_CUDA;
         }
         attr_set = true;
@@ -538,8 +618,11 @@ extern "C" int mrb_gemm_tc(const float* A, int lda, int M, int K, const void* im
     Params p;
     p.A = A; p.lda = lda; p.M = M; p.K = K; p.image = (const unsigned char*)image; p.N = N; p.NT = pl.NT;
     p.nchunks = pl.nchunks; p.tmem_cols = pl.tmem_cols; p.nacc = pl.nacc; p.C = C; p.ldc = ldc;
-    dim3 grid(ceil_div(M, BM), pl.ntiles);
-    k_gemm_tc<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(p);
+    p.acc_bufs = (2 * pl.nacc * pl.tmem_cols <= 512) ? 2 : 1;
+    p.mtiles = ceil_div(M, BM);
+    p.ntiles = pl.ntiles;
+    const int grid = min(p.mtiles * p.ntiles, kNumSMs);
+    k_gemm_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream_>>>(p);
     return check_launch("gemm_tc");
 }
 
