@@ -105,11 +105,13 @@ int mrb_gemm_tc_wgrad(const float* X, int ldx, const float* G, int ldg, int V, i
  *   fmap       n_img x C x Hm x Wm fp32 (NCHW, Hm == Wm)
  *   pos        SV x 3;  vert_mesh[v] = mesh of vertex v;  mesh_info[mesh] = {image index, image H, image W}
  *   out        SV x ld_out (this map's channels are written at out[v*ld_out + 0..C-1]; pass a column-offset pointer)
+ *   workspace  n_img*C*Hm*Wm floats (channels-last copy of the map for the TMA bulk-copy gather); NULL selects the
+ *              register path
  * Backward: gfmap[img,c,x1,y1] += gout[v,c] (atomic fp32); vertex positions receive no gradient (as in the
  * reference, where the integer cast at layers.py:592 cuts the graph).
  */
 int mrb_vert_align_fwd(const float* fmap, int n_img, int C, int Hm, int Wm, const float* pos, const int32_t* vert_mesh,
-                       const int32_t* mesh_info, int SV, float* out, int ld_out, void* stream);
+                       const int32_t* mesh_info, int SV, float* out, int ld_out, float* workspace, void* stream);
 int mrb_vert_align_bwd(const float* gout, int ld_g, int n_img, int C, int Hm, int Wm, const float* pos,
                        const int32_t* vert_mesh, const int32_t* mesh_info, int SV, float* gfmap, void* stream);
 

@@ -308,8 +308,9 @@ class _VertAlign(torch.autograd.Function):
         off = 0
         for m in maps:
             n_img, C, Hm, Wm = m.shape
+            ws = torch.empty_like(m)          # channels-last copy for the TMA gather
             _lib.call("mrb_vert_align_fwd", _lib.ptr(m), n_img, C, Hm, Wm, _lib.ptr(pos_c), _lib.ptr(vert_mesh),
-                      _lib.ptr(mesh_info), SV, _lib.ptr(out) + 4 * off, ctot)
+                      _lib.ptr(mesh_info), SV, _lib.ptr(out) + 4 * off, ctot, _lib.ptr(ws))
             off += C
         ctx.save_for_backward(pos_c, vert_mesh, mesh_info)
         ctx.shapes = [tuple(m.shape) for m in maps]
