@@ -27,39 +27,66 @@ constexpr int SORT_MAX = 16384; // clouds up to this size are x-sorted in shared
 // ---------------------------------------------------------------------------------------------------------
 // stage 0: per-cloud sort by the x coordinate (bitonic, one CTA per cloud) -> float4 (x, y, z, original index)
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t sortable(float x) {
-    const uint32_t u = __float_as_uint(x);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
+constexpr int NBUCKET = 2048;
 
-__global__ void __launch_bounds__(1024) k_sort_x(const float* __restrict__ pts, int P, int N2, float4* __restrict__ out) {
+// One CTA per cloud: counting sort of the points into NBUCKET uniform x buckets (O(n): histogram with shared-memory
+// atomics, block scan, scatter).  The order inside a bucket is arbitrary -- the scan kernel does not need a total order,
+// only tiles (runs of TILE packed points) that are compact in x; their exact x ranges are written to `trange`.
+// out: float4 (x, y, z, original index);  trange: [tile] (xmin, xmax).
+__global__ void __launch_bounds__(1024) k_sort_x(const float* __restrict__ pts, int P, float4* __restrict__ out,
+                                                 float2* __restrict__ trange, int ntiles) {
     extern __shared__ unsigned char smem_raw[];
-    uint32_t* key = reinterpret_cast<uint32_t*>(smem_raw);
-    unsigned short* idx = reinterpret_cast<unsigned short*>(key + N2);
+    int* counts = reinterpret_cast<int*>(smem_raw);                 // [NBUCKET] histogram -> exclusive offsets -> cursors
+    float* xs = reinterpret_cast<float*>(counts + NBUCKET);        // [P] x of the packed order
+    __shared__ float s_lo[32], s_hi[32];
+    __shared__ int s_scan[33];
     const float* src = pts + (size_t)blockIdx.x * P * 3;
-    for (int i = threadIdx.x; i < N2; i += blockDim.x) {
-        key[i] = (i < P) ? sortable(src[3 * (size_t)i]) : 0xffffffffu;
-        idx[i] = (unsigned short)i;
+    float lo = FLT_MAX, hi = -FLT_MAX;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const float x = src[3 * (size_t)i];
+        lo = fminf(lo, x); hi = fmaxf(hi, x);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (lane_id() == 0) { s_lo[warp_id()] = lo; s_hi[warp_id()] = hi; }
+    for (int i = threadIdx.x; i < NBUCKET; i += blockDim.x) counts[i] = 0;
+    __syncthreads();
+    for (int w = 0; w < 32; ++w) { lo = fminf(lo, s_lo[w]); hi = fmaxf(hi, s_hi[w]); }
+    const float scale = (hi > lo) ? (float)NBUCKET / (hi - lo) : 0.f;
+    auto bucket_of = [&](float x) { return min(NBUCKET - 1, max(0, (int)((x - lo) * scale))); };
+    for (int i = threadIdx.x; i < P; i += blockDim.x) atomicAdd(&counts[bucket_of(src[3 * (size_t)i])], 1);
+    __syncthreads();
+    // exclusive scan of the NBUCKET counts: 2 per thread
+    {
+        const int a = counts[2 * threadIdx.x], b2 = counts[2 * threadIdx.x + 1];
+        int total;
+        const int ex = block_exclusive_scan(a + b2, s_scan, &total);
+        __syncthreads();
+        counts[2 * threadIdx.x] = ex;
+        counts[2 * threadIdx.x + 1] = ex + a;
     }
     __syncthreads();
-    for (int k = 2; k <= N2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < (N2 >> 1); t += blockDim.x) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // lower index of the pair (bit j clear)
-                const int l = i | j;
-                const bool up = (i & k) == 0;
-                const uint32_t ka = key[i], kb = key[l];
-                const unsigned short ia = idx[i], ib = idx[l];
-                const bool gt = ka > kb || (ka == kb && ia > ib);       // (key, original index): total, deterministic order
-                if (gt == up) { key[i] = kb; key[l] = ka; idx[i] = ib; idx[l] = ia; }
-            }
-            __syncthreads();
-        }
-    }
     float4* dst = out + (size_t)blockIdx.x * P;
     for (int i = threadIdx.x; i < P; i += blockDim.x) {
-        const int o = idx[i];
-        dst[i] = make_float4(src[3 * (size_t)o], src[3 * (size_t)o + 1], src[3 * (size_t)o + 2], __int_as_float(o));
+        const float x = src[3 * (size_t)i];
+        const int pos = atomicAdd(&counts[bucket_of(x)], 1);
+        dst[pos] = make_float4(x, src[3 * (size_t)i + 1], src[3 * (size_t)i + 2], __int_as_float(i));
+        xs[pos] = x;
+    }
+    __syncthreads();
+    float2* tr = trange + (size_t)blockIdx.x * ntiles;
+    for (int t = warp_id(); t < ntiles; t += blockDim.x >> 5) {
+        float tlo = FLT_MAX, thi = -FLT_MAX;
+        for (int i = t * TILE + lane_id(); i < min((t + 1) * TILE, P); i += 32) { tlo = fminf(tlo, xs[i]); thi = fmaxf(thi, xs[i]); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            tlo = fminf(tlo, __shfl_xor_sync(0xffffffffu, tlo, o));
+            thi = fmaxf(thi, __shfl_xor_sync(0xffffffffu, thi, o));
+        }
+        if (lane_id() == 0) tr[t] = make_float2(tlo, thi);
     }
 }
 
@@ -132,12 +159,13 @@ struct Query {
 //   a conservative *filter* whose rounding error is covered by `margin`; hits are queued (2 bytes) and re-evaluated
 //   exactly when a queue fills (warp-wide) or the tile ends, so results equal an exact scan while the divergent
 //   sorted-list insertion stays out of the inner loop.
-// * Pruning: both clouds are sorted by x, a CTA's queries span a narrow x range, candidate tiles are visited outwards
+// * Pruning: both clouds are bucket-sorted by x, a CTA's queries span a narrow x range, candidate tiles are visited outwards
 //   from that range, and a direction is abandoned once the tile's x gap alone exceeds every query's current k-th best
 //   distance.  The scan stays exact (the bound is a true lower bound of the distance).
 template <int K>
-__global__ void __launch_bounds__(THREADS) k_nn(const float4* __restrict__ a, const float4* __restrict__ b, int P, int Q,
-                                                int prune, float* __restrict__ min_d, int32_t* __restrict__ min_i,
+__global__ void __launch_bounds__(THREADS) k_nn(const float4* __restrict__ a, const float4* __restrict__ b,
+                                                const float2* __restrict__ trange_b, int P, int Q, int prune,
+                                                float* __restrict__ min_d, int32_t* __restrict__ min_i,
                                                 int32_t* __restrict__ knn, int k_out) {
     __shared__ float4 tile[TILE + STEP];
     __shared__ int tile_idx[TILE];
@@ -179,15 +207,11 @@ __global__ void __launch_bounds__(THREADS) k_nn(const float4* __restrict__ a, co
     xlo = blk[0]; xhi = blk[1];
 
     const int ntiles = (Q + TILE - 1) / TILE;
-    // first tile: the one holding the first candidate with x >= xlo (binary search over the sorted cloud)
+    const float2* tr = trange_b + (size_t)batch * ntiles;
+    // first tile: the first one whose x range reaches the query range
     int start = 0;
     if (prune) {
-        int lo = 0, hi = Q;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (bq[mid].x < xlo) lo = mid + 1; else hi = mid;
-        }
-        start = min(lo, Q - 1) / TILE;
+        while (start + 1 < ntiles && tr[start].y < xlo) ++start;
     }
     int left = start - 1, right = start;       // next unvisited tile on each side
     bool left_open = prune != 0, right_open = true;
@@ -200,12 +224,12 @@ __global__ void __launch_bounds__(THREADS) k_nn(const float4* __restrict__ a, co
             const float thr_max = blk[2];
             float gl = FLT_MAX, gr = FLT_MAX;
             if (left_open && left >= 0) {
-                const float xl = bq[min((left + 1) * TILE, Q) - 1].x;      // largest x of the left tile
+                const float xl = tr[left].y;                                // largest x of the left tile
                 gl = fmaxf(xlo - xl, 0.f);
                 if (thr_max < FLT_MAX && gl * gl > thr_max) { left_open = false; gl = FLT_MAX; }
             } else left_open = false;
             if (right_open && right < ntiles) {
-                const float xr = bq[right * TILE].x;                        // smallest x of the right tile
+                const float xr = prune ? tr[right].x : 0.f;                 // smallest x of the right tile
                 gr = prune ? fmaxf(xr - xhi, 0.f) : 0.f;
                 if (thr_max < FLT_MAX && gr * gr > thr_max) { right_open = false; gr = FLT_MAX; }
             } else right_open = false;
@@ -331,24 +355,21 @@ __global__ void __launch_bounds__(256) k_chamfer_bwd(const float* __restrict__ a
 }
 
 template <int K>
-static void launch_nn(const float4* a, const float4* b, int B, int P, int Q, int prune, float* min_d, int32_t* min_i,
-                      int32_t* knn, int k, cudaStream_t s) {
-    k_nn<K><<<dim3(ceil_div(P, THREADS * QPT), B), THREADS, 0, s>>>(a, b, P, Q, prune, min_d, min_i, knn, k);
+static void launch_nn(const float4* a, const float4* b, const float2* trange_b, int B, int P, int Q, int prune, float* min_d,
+                      int32_t* min_i, int32_t* knn, int k, cudaStream_t s) {
+    k_nn<K><<<dim3(ceil_div(P, THREADS * QPT), B), THREADS, 0, s>>>(a, b, trange_b, P, Q, prune, min_d, min_i, knn, k);
 }
 
-static int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
-
-// packs (and x-sorts, when the cloud fits the shared-memory sort) B clouds of P points into float4 records
-static bool pack_cloud(const float* pts, int B, int P, float4* out, cudaStream_t s) {
+// packs (and x-bucket-sorts, when the cloud fits the shared-memory pass) B clouds of P points into float4 records
+static bool pack_cloud(const float* pts, int B, int P, float4* out, float2* trange, cudaStream_t s) {
     if (P <= SORT_MAX) {
-        const int N2 = max(next_pow2(P), 2);
-        const size_t smem = (size_t)N2 * 6;
+        const size_t smem = (size_t)NBUCKET * 4 + (size_t)P * 4;
         static bool attr_set = false;
         if (!attr_set) {
-            cudaFuncSetAttribute(k_sort_x, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_MAX * 6);
+            cudaFuncSetAttribute(k_sort_x, cudaFuncAttributeMaxDynamicSharedMemorySize, NBUCKET * 4 + SORT_MAX * 4);
             attr_set = true;
         }
-        k_sort_x<<<B, 1024, smem, s>>>(pts, P, N2, out);
+        k_sort_x<<<B, 1024, smem, s>>>(pts, P, out, trange, ceil_div(P, TILE));
         return true;
     }
     const long long n = (long long)B * P;
@@ -364,7 +385,8 @@ using namespace mrb::chamfer;
 
 extern "C" long long mrb_knn_workspace_bytes(int B, int P, int Q) {
     if (B < 0 || P < 0 || Q < 0) return -1;
-    return (long long)sizeof(float4) * ((long long)B * P + (long long)B * Q) + 256;
+    const long long tiles = (long long)B * (ceil_div(max(P, 1), TILE) + ceil_div(max(Q, 1), TILE));
+    return (long long)sizeof(float4) * ((long long)B * P + (long long)B * Q) + (long long)sizeof(float2) * tiles + 256;
 }
 
 extern "C" int mrb_knn_fwd(const float* a, const float* b, int B, int P, int Q, int k, float* min_d_a, int32_t* min_i_a,
@@ -381,12 +403,14 @@ extern "C" int mrb_knn_fwd(const float* a, const float* b, int B, int P, int Q, 
     cudaStream_t s = (cudaStream_t)stream_;
     float4* pa = reinterpret_cast<float4*>(((uintptr_t)workspace + 15) & ~(uintptr_t)15);
     float4* pb = pa + (size_t)B * P;
-    const bool sa = pack_cloud(a, B, P, pa, s);
-    const bool sb = pack_cloud(b, B, Q, pb, s);
+    float2* tra = reinterpret_cast<float2*>(pb + (size_t)B * Q);
+    float2* trb = tra + (size_t)B * ceil_div(P, TILE);
+    const bool sa = pack_cloud(a, B, P, pa, tra, s);
+    const bool sb = pack_cloud(b, B, Q, pb, trb, s);
 #define MRB_NN(KK)                                                                                        \
     do {                                                                                                  \
-        if (min_d_a) launch_nn<KK>(pa, pb, B, P, Q, sb ? 1 : 0, min_d_a, min_i_a, knn_a, k, s);           \
-        if (min_d_b) launch_nn<KK>(pb, pa, B, Q, P, sa ? 1 : 0, min_d_b, min_i_b, knn_b, k, s);           \
+        if (min_d_a) launch_nn<KK>(pa, pb, trb, B, P, Q, sb ? 1 : 0, min_d_a, min_i_a, knn_a, k, s);      \
+        if (min_d_b) launch_nn<KK>(pb, pa, tra, B, Q, P, sa ? 1 : 0, min_d_b, min_i_b, knn_b, k, s);      \
     } while (0)
     if (k <= 1) MRB_NN(1);
     else if (k <= 4) MRB_NN(4);
