@@ -72,6 +72,10 @@ int mrb_csr_gather_fwd(const int32_t* rowptr, const int32_t* col, int n, const f
 int mrb_relu_mask(const float* gout, int ld_g, const float* act, int ld_a, int n, int D, float* gz, int ld_z,
                   void* stream);
 int mrb_segment_ids(const int32_t* offsets, int nseg, int n, int32_t* ids, void* stream);
+/* Fused backward of GraphConv's add + ReLU + aggregation (layers.py:63-68): gy[:, 0:D] = gz, gy[:, D:2D] = A^T gz with
+ * gz = gout * (act > 0) formed on the fly (gout may be a strided view: ld_g >= D). */
+int mrb_graphconv_bwd_gather(const int32_t* rowptr_t, const int32_t* col_t, int n, const float* gout, int ld_g,
+                             const float* act, int ld_a, int D, float* gy, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Dense contraction  C = op(A) * op(B) + beta * C  (row-major fp32, exact fp32 accumulate on the CUDA cores).

@@ -145,6 +145,43 @@ __global__ void k_relu_mask(const float* __restrict__ gout, int ld_g, const floa
     gz[(size_t)row * ld_z + d] = a > 0.f ? gout[(size_t)row * ld_g + d] : 0.f;
 }
 
+// Backward of relu(self + sum_nbr): gz = gout * (act > 0) is formed on the fly, written to gy[:, 0:D] and gathered over the
+// transposed adjacency into gy[:, D:2D] -- one pass instead of a mask kernel plus a gather kernel.
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_gather_bwd(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int n,
+                                                    const float* __restrict__ gout, int ld_g, const float* __restrict__ act,
+                                                    int ld_a, int D, float* __restrict__ gy) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    if (row >= n) return;
+    const int beg = rowptr[row], end = rowptr[row + 1];
+    auto masked = [&](int r, int d) {
+        float4 g, a;
+        if (VEC) {
+            g = __ldg(reinterpret_cast<const float4*>(gout + (size_t)r * ld_g + d));
+        } else {
+            const float* gp = gout + (size_t)r * ld_g + d;
+            g = make_float4(__ldg(gp), __ldg(gp + 1), __ldg(gp + 2), __ldg(gp + 3));
+        }
+        a = __ldg(reinterpret_cast<const float4*>(act + (size_t)r * ld_a + d));
+        return make_float4(a.x > 0.f ? g.x : 0.f, a.y > 0.f ? g.y : 0.f, a.z > 0.f ? g.z : 0.f, a.w > 0.f ? g.w : 0.f);
+    };
+    for (int d = lane_id() * 4; d < D; d += 128) {
+        *reinterpret_cast<float4*>(gy + (size_t)row * 2 * D + d) = masked(row, d);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int j = beg;
+        for (; j + 1 < end; j += 2) {
+            const float4 x = masked(col[j], d), y = masked(col[j + 1], d);
+            acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+            acc.x += y.x; acc.y += y.y; acc.z += y.z; acc.w += y.w;
+        }
+        if (j < end) {
+            const float4 x = masked(col[j], d);
+            acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+        }
+        *reinterpret_cast<float4*>(gy + (size_t)row * 2 * D + D + d) = acc;
+    }
+}
+
 __global__ void k_segment_ids(const int32_t* __restrict__ offsets, int nseg, int n, int32_t* __restrict__ ids) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -215,4 +252,17 @@ extern "C" int mrb_segment_ids(const int32_t* offsets, int nseg, int n, int32_t*
     if (n == 0) return MRB_OK;
     k_segment_ids<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream_>>>(offsets, nseg, n, ids);
     return check_launch("segment_ids");
+}
+
+extern "C" int mrb_graphconv_bwd_gather(const int32_t* rowptr_t, const int32_t* col_t, int n, const float* gout, int ld_g,
+                                        const float* act, int ld_a, int D, float* gy, void* stream_) {
+    MRB_REQUIRE(rowptr_t && col_t && gout && act && gy, "graphconv_bwd_gather: null pointer");
+    MRB_REQUIRE(D % 4 == 0 && ld_a % 4 == 0 && ((uintptr_t)act % 16 == 0) && ((uintptr_t)gy % 16 == 0),
+                "graphconv_bwd_gather: D and the activation rows must be 16-byte aligned");
+    if (n == 0) return MRB_OK;
+    cudaStream_t s = (cudaStream_t)stream_;
+    const bool vec = (ld_g % 4 == 0) && ((uintptr_t)gout % 16 == 0);
+    if (vec) k_gather_bwd<true><<<ceil_div(n, 8), 256, 0, s>>>(rowptr_t, col_t, n, gout, ld_g, act, ld_a, D, gy);
+    else k_gather_bwd<false><<<ceil_div(n, 8), 256, 0, s>>>(rowptr_t, col_t, n, gout, ld_g, act, ld_a, D, gy);
+    return check_launch("graphconv_bwd_gather");
 }

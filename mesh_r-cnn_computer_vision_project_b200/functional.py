@@ -253,13 +253,20 @@ class _GraphConv(torch.autograd.Function):
     def backward(ctx, gout):
         x, w0, w1, out = ctx.saved_tensors
         topo = ctx.topo
-        gout = _f32c(gout)
         n, K = x.shape
         D = w0.shape[1]
+        # upstream gradients are often column slices of a wider matrix (autograd of torch.cat): read them in place
+        if gout.dtype != torch.float32 or gout.stride(1) != 1 or gout.stride(0) < D:
+            gout = _f32c(gout)
+        ld_g = gout.stride(0)
         gy = torch.empty(n, 2 * D, dtype=torch.float32, device=x.device)
         gp = _lib.ptr(gy)
-        _lib.call("mrb_relu_mask", _lib.ptr(gout), D, _lib.ptr(out), D, n, D, gp, 2 * D)
-        _gather(topo.rowptr_t, topo.col_t, n, None, 0, gp, 2 * D, D, False, gp + 4 * D, 2 * D)
+        if D % 4 == 0:
+            _lib.call("mrb_graphconv_bwd_gather", _lib.ptr(topo.rowptr_t), _lib.ptr(topo.col_t), n, gout.data_ptr(), ld_g,
+                      _lib.ptr(out), D, D, gp)
+        else:
+            _lib.call("mrb_relu_mask", gout.data_ptr(), ld_g, _lib.ptr(out), D, n, D, gp, 2 * D)
+            _gather(topo.rowptr_t, topo.col_t, n, None, 0, gp, 2 * D, D, False, gp + 4 * D, 2 * D)
         gx = gw0 = gw1 = None
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)
