@@ -17,11 +17,11 @@
 namespace mrb {
 namespace chamfer {
 
-constexpr int TILE = 512;       // candidate points staged per shared-memory tile
-constexpr int THREADS = 128;    // threads per CTA
-constexpr int QPT = 2;          // query points per thread (one LDS.128 of a candidate feeds both)
-constexpr int QCAP = 16;        // deferred-hit queue entries per query
-constexpr int STEP = 4;         // candidates between two warp-wide queue checks
+constexpr int TILE = 256;       // candidate points staged per shared-memory tile
+constexpr int THREADS = 64;     // threads per CTA
+constexpr int QPT = 1;          // query points per thread (one LDS.128 of a candidate feeds both)
+constexpr int QCAP = 24;        // deferred-hit queue entries per query
+constexpr int STEP = 8;         // candidates between two warp-wide queue checks
 constexpr int SORT_MAX = 16384; // clouds up to this size are x-sorted in shared memory (pruned scan)
 
 // ---------------------------------------------------------------------------------------------------------
