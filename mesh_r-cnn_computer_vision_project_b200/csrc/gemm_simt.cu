@@ -92,6 +92,74 @@ __global__ void k_scale_rows(float* __restrict__ C, int M, int N, int ldc, float
     *c = (beta == 0.f) ? 0.f : *c * beta;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// skinny shapes of the 3-wide position heads (128 -> 3, 131 -> 3): one of the GEMM dimensions is <= 8
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SKINNY = 8;
+
+// C[M x N] = A[M x K] * B[N x K]^T, N <= 8: one warp per row, lanes stride over K, N accumulators, warp reduce
+__global__ void __launch_bounds__(256) k_skinny_nt(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                   const float* __restrict__ B, int ldb, float beta, float* __restrict__ C,
+                                                   int ldc) {
+    const int m = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    if (m >= M) return;
+    float acc[SKINNY];
+#pragma unroll
+    for (int n = 0; n < SKINNY; ++n) acc[n] = 0.f;
+    for (int k = lane_id(); k < K; k += 32) {
+        const float a = A[(size_t)m * lda + k];
+#pragma unroll
+        for (int n = 0; n < SKINNY; ++n)
+            if (n < N) acc[n] = fmaf(a, __ldg(B + (size_t)n * ldb + k), acc[n]);
+    }
+#pragma unroll
+    for (int n = 0; n < SKINNY; ++n) acc[n] = warp_sum(acc[n]);
+    if (lane_id() < N) {
+        float v = 0.f;
+#pragma unroll
+        for (int n = 0; n < SKINNY; ++n)
+            if (n == lane_id()) v = acc[n];
+        float* c = C + (size_t)m * ldc + lane_id();
+        *c = (beta == 0.f) ? v : fmaf(beta, *c, v);
+    }
+}
+
+// C[M x N] = A[M x K] * B[K x N], K <= 8: one thread per output element
+__global__ void __launch_bounds__(256) k_skinny_k(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                  const float* __restrict__ B, int ldb, float beta, float* __restrict__ C,
+                                                  int ldc) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)M * N) return;
+    const int m = (int)(t / N), n = (int)(t % N);
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < SKINNY; ++k)
+        if (k < K) acc = fmaf(A[(size_t)m * lda + k], __ldg(B + (size_t)k * ldb + n), acc);
+    float* c = C + (size_t)m * ldc + n;
+    *c = (beta == 0.f) ? acc : fmaf(beta, *c, acc);
+}
+
+// C[M x N] += A[K x M]^T * B[K x N], M <= 8 (C pre-scaled by beta): blocks own chunks of the long K dimension
+__global__ void __launch_bounds__(256) k_skinny_tn(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                   const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
+                                                   int rows_per_block) {
+    const int k0 = blockIdx.x * rows_per_block, k1 = min(K, k0 + rows_per_block);
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        float acc[SKINNY];
+#pragma unroll
+        for (int m = 0; m < SKINNY; ++m) acc[m] = 0.f;
+        for (int k = k0; k < k1; ++k) {
+            const float b = B[(size_t)k * ldb + n];
+#pragma unroll
+            for (int m = 0; m < SKINNY; ++m)
+                if (m < M) acc[m] = fmaf(__ldg(A + (size_t)k * lda + m), b, acc[m]);
+        }
+#pragma unroll
+        for (int m = 0; m < SKINNY; ++m)
+            if (m < M) atomicAdd(C + (size_t)m * ldc + n, acc[m]);
+    }
+}
+
 }  // namespace gemm
 }  // namespace mrb
 
@@ -104,6 +172,20 @@ extern "C" int mrb_sgemm(int transA, int transB, int M, int N, int K, const floa
     MRB_REQUIRE(M >= 0 && N >= 0 && K >= 0, "sgemm: negative dimension");
     if (M == 0 || N == 0) return MRB_OK;
     cudaStream_t s = (cudaStream_t)stream_;
+    if (K > 0 && !transA && transB && N <= SKINNY) {
+        k_skinny_nt<<<ceil_div(M, 8), 256, 0, s>>>(M, N, K, A, lda, B, ldb, beta, C, ldc);
+        return check_launch("sgemm");
+    }
+    if (K > 0 && !transA && !transB && K <= SKINNY) {
+        k_skinny_k<<<(unsigned)ceil_div64((long long)M * N, 256), 256, 0, s>>>(M, N, K, A, lda, B, ldb, beta, C, ldc);
+        return check_launch("sgemm");
+    }
+    if (K > 0 && transA && !transB && M <= SKINNY) {
+        k_scale_rows<<<(unsigned)ceil_div64((long long)M * N, 256), 256, 0, s>>>(C, M, N, ldc, beta);
+        const int rpb = max(64, ceil_div(K, 4 * kNumSMs));
+        k_skinny_tn<<<ceil_div(K, rpb), 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, rpb);
+        return check_launch("sgemm");
+    }
     const int gx = ceil_div(N, BN), gy = ceil_div(M, BM);
     // split-K when the output tile grid cannot fill the machine and K is long (weight gradients: K = #vertices)
     int splits = 1;

@@ -74,3 +74,21 @@ def test_tc_wgrad(lib, V, Kin, N, split):
     got = torch.cat([c0, c1], 1) if c1 is not None else c0
     err = float((got.cpu().double() - want).abs().max())
     assert err <= 1e-5 * float(want.abs().max()), (V, Kin, N, err, float(want.abs().max()))
+
+
+@pytest.mark.parametrize("ta,tb,M,N,K", [(0, 1, 5000, 3, 131), (0, 0, 5000, 131, 3), (1, 0, 3, 131, 5000), (0, 1, 77, 8, 40),
+                                         (1, 0, 8, 300, 999), (0, 0, 100, 50, 70), (1, 1, 33, 65, 129), (1, 0, 131, 128, 4000)])
+def test_sgemm_simt_all_paths(lib, ta, tb, M, N, K):
+    """Exact-fp32 CUDA-core GEMM incl. the skinny special cases of the 3-wide heads, with beta accumulation."""
+    from meshrcnn_b200 import _lib
+    g = torch.Generator().manual_seed(M * 7 + N)
+    a = torch.randn((K, M) if ta else (M, K), generator=g)
+    b = torch.randn((N, K) if tb else (K, N), generator=g)
+    c0 = torch.randn(M, N, generator=g)
+    for beta in (0.0, 1.0):
+        c = c0.clone().cuda()
+        ad, bd = a.cuda(), b.cuda()
+        _lib.call("mrb_sgemm", ta, tb, M, N, K, _lib.ptr(ad), a.shape[1], _lib.ptr(bd), b.shape[1], beta, _lib.ptr(c), N)
+        want = (a.t() if ta else a).double() @ (b.t() if tb else b).double() + beta * c0.double()
+        err = float((c.cpu().double() - want).abs().max())
+        assert err <= 2e-6 * float(want.abs().max()) * max(1.0, (K / 100) ** 0.5), (ta, tb, M, N, K, beta, err)
