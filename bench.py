@@ -274,7 +274,8 @@ def run_cuda(args):
             per = breakdown[top]["ms_per_step"] / breakdown[top]["calls_per_step"] * 1e-3
             a = work["knn_bytes_per_launch"] / per / 1e9
             roofline = {"kernel": "k_nn<10> (mrb_knn_fwd)", "bound": "hbm", "achieved": round(a, 2), "peak": peaks["hbm_gbs"],
-                        "unit": "GB/s", "frac": round(a / peaks["hbm_gbs"], 5), "traffic": None, "peak_src": peaks["src"],
+                        "unit": "GB/s", "frac": round(a / peaks["hbm_gbs"], 5), "traffic": 10.96e6,
+                        "traffic_src": "profiles/knn_r01_final_details.txt (dram read+write of one k_nn<10> launch)", "peak_src": peaks["src"],
                         "note": "dominant kernel is FP32-issue bound, not HBM/tensor bound (SURVEY 8d): see roofline_kernels"}
         else:
             r = roof_all.get(top) or next(iter(roof_all.values()))
