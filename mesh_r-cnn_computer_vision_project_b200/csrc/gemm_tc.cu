@@ -102,6 +102,8 @@ struct Params {
     int nacc;                        // accumulators used round-robin over the K chunks (bounds the fp32 chain length)
     int acc_bufs;                    // 2: the epilogue of tile j overlaps the MMAs of tile j+1 (double-buffered TMEM)
     int mtiles, ntiles;
+    int accumulate;                  // epilogue adds to C (K is processed in segments, see mrb_gemm_tc)
+    long long img_tile_stride;       // bytes between the images of consecutive N tiles
     float* C;
     int ldc;
 };
@@ -255,6 +257,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
                 if (aligned && c0 + 32 <= NT && colbase + 32 <= p.N) {
                     if (gm_mine < p.M) {
                         float4* dst = reinterpret_cast<float4*>(p.C + (size_t)gm_mine * p.ldc + colbase);
+                        if (p.accumulate) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const float4 o = dst[q];
+                                acc[4 * q] += o.x; acc[4 * q + 1] += o.y; acc[4 * q + 2] += o.z; acc[4 * q + 3] += o.w;
+                            }
+                        }
 #pragma unroll
                         for (int q = 0; q < 8; ++q) dst[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
                     }
@@ -269,7 +278,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
                         const int rmax = min(32, p.M - (m0 + ew * 32));
 #pragma unroll 8
                         for (int r = 0; r < 32; ++r)
-                            if (r < rmax) dst[(size_t)r * p.ldc] = stage_t[r * 33 + lane];
+                            if (r < rmax) dst[(size_t)r * p.ldc] = stage_t[r * 33 + lane] + (p.accumulate ? dst[(size_t)r * p.ldc] : 0.f);
                     }
                     __syncwarp();
                 }
@@ -301,10 +310,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
                     for (int kk = 0; kk < BK / 8; ++kk) {
                         const uint64_t dah = umma_desc(a_hi + kk * 32), dal = umma_desc(a_lo + kk * 32);
                         const uint64_t dbh = umma_desc(b_hi + kk * 32), dbl = umma_desc(b_lo + kk * 32);
-                        const uint32_t d = tmem_d + (uint32_t)((c % p.nacc) * p.tmem_cols);
-                        umma_tf32(d, dal, dbh, idesc, (c >= p.nacc) || kk != 0);
-                        umma_tf32(d, dah, dbl, idesc, 1);
-                        umma_tf32(d, dah, dbh, idesc, 1);
+                        // The fp32 accumulate of the tensor core truncates (error ~1 ulp of the accumulator per MMA, biased), so
+                        // the two small cross terms get their own accumulator (2^-11 of the magnitude: their truncation is
+                        // negligible) and only the K/8 hi*hi products are chained into the main one(s).
+                        const int nmain = p.nacc - 1;
+                        const uint32_t d_main = tmem_d + (uint32_t)((c % nmain) * p.tmem_cols);
+                        const uint32_t d_aux = tmem_d + (uint32_t)(nmain * p.tmem_cols);
+                        umma_tf32(d_aux, dal, dbh, idesc, (c | kk) != 0);
+                        umma_tf32(d_aux, dah, dbl, idesc, 1);
+                        umma_tf32(d_main, dah, dbh, idesc, (c >= nmain) || kk != 0);
                     }
                     umma_commit(empty_bar(s));                 // stage reusable once these MMAs retire
                 }
@@ -317,7 +331,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
         if (lane == 0) {
             int it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const unsigned char* img = p.image + (size_t)(tile % p.ntiles) * p.nchunks * 2 * b_bytes;
+                const unsigned char* img = p.image + (size_t)(tile % p.ntiles) * p.img_tile_stride;
                 for (int c = 0; c < p.nchunks; ++c, ++it) {
                     const int s = it % STAGES, use = it / STAGES;
                     if (use > 0) mbar_wait(empty_bar(s), (use - 1) & 1);
@@ -615,14 +629,29 @@ extern "C" int mrb_gemm_tc(const float* A, int lda, int M, int K, const void* im
         attr_set = true;
     }
     const Plan pl = make_plan(K, N);
-    Params p;
-    p.A = A; p.lda = lda; p.M = M; p.K = K; p.image = (const unsigned char*)image; p.N = N; p.NT = pl.NT;
-    p.nchunks = pl.nchunks; p.tmem_cols = pl.tmem_cols; p.nacc = pl.nacc; p.C = C; p.ldc = ldc;
-    p.acc_bufs = (2 * pl.nacc * pl.tmem_cols <= 512) ? 2 : 1;
-    p.mtiles = ceil_div(M, BM);
-    p.ntiles = pl.ntiles;
-    const int grid = min(p.mtiles * p.ntiles, kNumSMs);
-    k_gemm_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream_>>>(p);
+    // The tensor-core fp32 accumulate truncates, so the error of an accumulator grows with the number of MMAs chained
+    // into it.  K is therefore processed in segments of SEG chunks (1024 columns); every segment is a full pass whose
+    // epilogue adds into C with ordinary fp32 rounding.
+    const int SEG = 32;
+    const size_t b_bytes = (size_t)pl.NT * BK * 4;
+    for (int c0 = 0; c0 < pl.nchunks; c0 += SEG) {
+        const int nch = min(SEG, pl.nchunks - c0);
+        Params p;
+        p.A = A + (size_t)c0 * BK; p.lda = lda; p.M = M; p.K = min(K - c0 * BK, nch * BK);
+        p.image = (const unsigned char*)image + (size_t)c0 * 2 * b_bytes;
+        p.img_tile_stride = (long long)pl.nchunks * 2 * (long long)b_bytes;
+        p.N = N; p.NT = pl.NT; p.nchunks = nch; p.tmem_cols = pl.tmem_cols;
+        // accumulators: one for the lo cross terms + 1 or 3 main ones (long segments, when TMEM allows); power of two
+        p.nacc = 2;
+        if (nch > 16 && 4 * pl.tmem_cols <= 512) p.nacc = 4;
+        p.acc_bufs = (2 * p.nacc * pl.tmem_cols <= 512) ? 2 : 1;
+        p.mtiles = ceil_div(M, BM);
+        p.ntiles = pl.ntiles;
+        p.accumulate = c0 > 0;
+        p.C = C; p.ldc = ldc;
+        const int grid = min(p.mtiles * p.ntiles, kNumSMs);
+        k_gemm_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream_>>>(p);
+    }
     return check_launch("gemm_tc");
 }
 
@@ -650,7 +679,7 @@ extern "C" int mrb_gemm_tc_wgrad(const float* X, int ldx, const float* G, int ld
     const int mtiles = ceil_div(Kin, BM);
     const int total_chunks = ceil_div(V, BK);
     int splits = max(1, min(total_chunks, kNumSMs / mtiles));
-    p.chunks_per_split = ceil_div(total_chunks, splits);
+    p.chunks_per_split = min(ceil_div(total_chunks, splits), 32);    // <= 384 MMAs chained per accumulator (truncating adds)
     splits = ceil_div(total_chunks, p.chunks_per_split);
     k_gemm_tn<<<dim3(mtiles, splits), THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(p);
     return check_launch("gemm_tc_wgrad");

@@ -34,7 +34,9 @@ def _check(M, K, N, lda_pad=0, ldc_pad=0, split=None, transposed_src=False, seed
     got = c[:, :N].cpu().double()
     scale = float(want.abs().max())
     err = float((got - want).abs().max())
-    assert err <= 1e-5 * scale, (M, K, N, err, scale)    # tensor-core fp32 accumulation truncates: ~6e-8 * (#chained MMAs)
+    assert err <= 1e-5 * scale, (M, K, N, err, scale)
+    rel = float((got - want).norm() / want.norm())
+    assert rel <= 2e-6, (M, K, N, rel)          # 3xTF32 with a separate accumulator for the cross terms: ~6e-7 (IEEE fp32: ~3e-7)
     if ldc_pad:
         assert bool((c[:, N:] == -7.0).all())          # no write outside the N columns
 
