@@ -21,7 +21,7 @@ constexpr int TILE = 256;       // candidate points staged per shared-memory til
 constexpr int THREADS = 64;     // threads per CTA
 constexpr int QPT = 1;          // query points per thread (one LDS.128 of a candidate feeds both)
 constexpr int QCAP = 24;        // deferred-hit queue entries per query
-constexpr int STEP = 8;         // candidates between two warp-wide queue checks
+constexpr int STEP = 8;         // candidates per group (8-bit hit mask) between two warp-wide queue checks
 constexpr int SORT_MAX = 16384; // clouds up to this size are x-sorted in shared memory (pruned scan)
 
 // ---------------------------------------------------------------------------------------------------------
@@ -262,21 +262,29 @@ __global__ void __launch_bounds__(THREADS) k_nn(const float4* __restrict__ a, co
         // STEP candidates per iteration, then one warp-uniform vote: queues are drained by the whole warp together
         // (a lane draining alone would serialise the ~70-instruction insertion across the 32 lanes).
         for (int t0 = 0; t0 < cnt; t0 += STEP) {
+            unsigned hit[QPT];
+#pragma unroll
+            for (int u = 0; u < QPT; ++u) hit[u] = 0u;
 #pragma unroll
             for (int tt = 0; tt < STEP; ++tt) {
                 const float4 c = tile[t0 + tt];
 #pragma unroll
                 for (int u = 0; u < QPT; ++u) {
                     const float s = fmaf(qr[u].x, c.x, fmaf(qr[u].y, c.y, fmaf(qr[u].z, c.z, c.w)));
-                    if (s < qr[u].thr) {
-                        queue[u][qr[u].cnt * THREADS + tid] = (unsigned short)(t0 + tt);
-                        ++qr[u].cnt;
-                    }
+                    if (s < qr[u].thr) hit[u] |= 1u << tt;             // one predicated LOP per pair, no address math
                 }
             }
-            int fullest = qr[0].cnt;
+            int fullest = 0;
 #pragma unroll
-            for (int u = 1; u < QPT; ++u) fullest = max(fullest, qr[u].cnt);
+            for (int u = 0; u < QPT; ++u) {
+                unsigned m = hit[u];
+                while (m) {                                              // usually zero or one bit
+                    queue[u][qr[u].cnt * THREADS + tid] = (unsigned short)(t0 + __ffs(m) - 1);
+                    ++qr[u].cnt;
+                    m &= m - 1;
+                }
+                fullest = max(fullest, qr[u].cnt);
+            }
             if (__any_sync(0xffffffffu, fullest > QCAP - STEP)) {
 #pragma unroll
                 for (int u = 0; u < QPT; ++u) qr[u].drain(tile, tile_idx, &queue[u][tid], margin[u]);
