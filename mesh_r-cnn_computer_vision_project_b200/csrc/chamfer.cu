@@ -20,8 +20,8 @@ namespace chamfer {
 constexpr int TILE = 256;       // candidate points staged per shared-memory tile
 constexpr int THREADS = 64;     // threads per CTA
 constexpr int QPT = 1;          // query points per thread (one LDS.128 of a candidate feeds both)
-constexpr int QCAP = 24;        // deferred-hit queue entries per query
-constexpr int STEP = 8;         // candidates per group (8-bit hit mask) between two warp-wide queue checks
+constexpr int QCAP = 48;        // deferred-hit queue entries per query
+constexpr int STEP = 32;         // candidates per group (32-bit hit mask) between two warp-wide queue checks
 constexpr int SORT_MAX = 16384; // clouds up to this size are x-sorted in shared memory (pruned scan)
 
 // ---------------------------------------------------------------------------------------------------------

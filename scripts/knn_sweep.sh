@@ -2,7 +2,7 @@
 set -e
 F=mesh_r-cnn_computer_vision_project_b200/csrc/chamfer.cu
 cp $F /tmp/chamfer_orig.cu
-for cfg in "512 64 1 16 4" "256 128 1 16 4" "256 64 1 16 4" "256 128 1 24 8" "256 64 1 24 8" "128 64 1 24 8" "256 32 1 24 8" "384 64 1 24 8"; do
+for cfg in "256 64 1 48 32" "256 64 1 64 32" "256 64 1 96 32" "128 64 1 64 32" "256 32 1 64 32"; do
   set -- $cfg
   sed -e "s/constexpr int TILE = [0-9]*;/constexpr int TILE = $1;/" -e "s/constexpr int THREADS = [0-9]*;/constexpr int THREADS = $2;/" \
       -e "s/constexpr int QPT = [0-9]*;/constexpr int QPT = $3;/" -e "s/constexpr int QCAP = [0-9]*;/constexpr int QCAP = $4;/" \
