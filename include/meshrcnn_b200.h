@@ -150,8 +150,11 @@ int mrb_sample_points_bwd(const float* gcloud, const float* cloud, const double*
  *   mrb_knn_fwd     both directions in one call: for each point of a (B x P x 3) the squared distance + index of the
  *                   nearest point of b (B x Q x 3) and, if k > 0 (k <= 16), the k nearest indices sorted by
  *                   (distance, index) -- outputs *_a -- and the same for each point of b against a -- outputs *_b
- *                   (either output set may be NULL).  Exact (direct (p-q)^2 distances); internally both clouds are
- *                   sorted by x so that far candidate tiles are pruned.  workspace: mrb_knn_workspace_bytes(B,P,Q).
+ *                   (either output set may be NULL).  Exact (direct (p-q)^2 distances).  Clouds of <= 65535 points are
+ *                   counting-sorted into a uniform cell grid and every query scans a growing cell box until its k-th
+ *                   best distance is proven final; larger clouds use the shared-memory tiled scan (x-sorted, far tiles
+ *                   pruned).  Both return identical results.  workspace: mrb_knn_workspace_bytes(B,P,Q).
+ *   mrb_knn_fwd_algo  same, with the search strategy forced: 0 automatic, 1 tiled scan, 2 cell grid.
  *   mrb_sum_scaled  out[0] = scale * sum(x[0..n))   (fp64 accumulation; acc = 1 double of scratch)
  *   mrb_chamfer_bwd gradient of  *g_a * scale * sum_i |a_i - b_idx_a[i]|^2 + *g_b * scale * sum_j |a_idx_b[j] - b_j|^2
  *                   accumulated into ga / gb (either may be NULL).
@@ -159,6 +162,9 @@ int mrb_sample_points_bwd(const float* gcloud, const float* cloud, const double*
 long long mrb_knn_workspace_bytes(int B, int P, int Q);
 int mrb_knn_fwd(const float* a, const float* b, int B, int P, int Q, int k, float* min_d_a, int32_t* min_i_a,
                 int32_t* knn_a, float* min_d_b, int32_t* min_i_b, int32_t* knn_b, void* workspace, void* stream);
+int mrb_knn_fwd_algo(const float* a, const float* b, int B, int P, int Q, int k, float* min_d_a, int32_t* min_i_a,
+                     int32_t* knn_a, float* min_d_b, int32_t* min_i_b, int32_t* knn_b, void* workspace, int algo,
+                     void* stream);
 int mrb_sum_scaled(const float* x, long long n, double scale, double* acc, float* out, void* stream);
 int mrb_chamfer_bwd(const float* a, const float* b, int B, int P, int Q, const int32_t* idx_a, const int32_t* idx_b,
                     const float* g_a, const float* g_b, float scale, float* ga, float* gb, void* stream);

@@ -319,6 +319,266 @@ __global__ void __launch_bounds__(THREADS) k_nn(const float4* __restrict__ a, co
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// grid path: exact k-NN through a uniform cell grid over the candidate cloud (default for clouds <= 65535 points)
+// ---------------------------------------------------------------------------------------------------------
+// The tiled scan above visits ~19 % of all pairs on the refinement workload (the x gap is a weak bound for points on a
+// surface).  Here each cloud is counting-sorted into G^3 cells (x fastest), so the points of cells [x0, x1] of one
+// (z, y) row are ONE contiguous run of the sorted array.  A query scans the rows of the cell box that covers
+// [q - r, q + r]; if the k-th best distance found is <= r^2 the result is final (every closer point lies inside the
+// box), otherwise r becomes that k-th distance (or doubles while fewer than k points were seen) and only the new
+// shell of cells is scanned.  ~60 candidates per query instead of ~1900, and the same (distance, index) order as the
+// brute-force scan, so both paths return identical results.
+//
+// Exactness under rounding: cell_of() is a monotone non-decreasing fp32 function (rn subtract, rn multiply by a
+// positive constant, floor, clamp) used for candidates and box corners alike, so a candidate whose coordinates lie in
+// [q - rr, q + rr] can never fall outside the cell box; rr exceeds r by 1e-5 relative, far above the ~4e-7 relative
+// rounding of the fp32 distance it is compared with.
+constexpr int GMAX = 32;                 // cells per axis (G^3 int counters must fit in shared memory)
+constexpr int GRID_MAX_POINTS = 65535;   // cell offsets are uint16
+constexpr int GRID_THREADS = 128;
+constexpr float GRID_C0 = 4.0f;          // first box sized for ~GRID_C0 * k points (measured best of 2..8 on B200)
+constexpr int CS_STRIDE = GMAX * GMAX * GMAX + 2;
+
+struct __align__(16) GridHdr {
+    float lo[3];
+    float r0;       // first search radius
+    float inv[3];   // cells per unit length (0 for a degenerate axis)
+    int G;
+};
+
+__device__ __forceinline__ int cell_of(float x, float lo, float inv, int G) {
+    return min(G - 1, max(0, __float2int_rd(__fmul_rn(__fsub_rn(x, lo), inv))));
+}
+
+static int grid_cells(int n) {
+    int g = (int)ceil(sqrt((double)n / 12.0));
+    return g < 1 ? 1 : (g > GMAX ? GMAX : g);
+}
+
+// One CTA per cloud (clouds of a first, then clouds of b): bounding box, cell histogram in shared memory, exclusive scan
+// (-> uint16 cell offsets), scatter into float4 (x, y, z, original index).  The order inside a cell is arbitrary; the
+// search result does not depend on it.  r0_scale = sqrt(c0 * k): the first box is sized to hold ~c0 * k points if the
+// cloud is a surface (occupied cells ~ box side^2).
+__global__ void __launch_bounds__(1024) k_grid_build(const float* __restrict__ pa, const float* __restrict__ pb, int B, int P,
+                                                     int Q, int Ga, int Gb, float4* __restrict__ oa, float4* __restrict__ ob,
+                                                     uint16_t* __restrict__ csa, uint16_t* __restrict__ csb,
+                                                     GridHdr* __restrict__ ha, GridHdr* __restrict__ hb, float r0_scale) {
+    extern __shared__ unsigned char smem_raw[];
+    int* counts = reinterpret_cast<int*>(smem_raw);
+    __shared__ float s_red[32][6];
+    __shared__ int s_scan[33];
+    const bool second = (int)blockIdx.x >= B;
+    const int cloud = second ? blockIdx.x - B : blockIdx.x;
+    const int n = second ? Q : P, G = second ? Gb : Ga;
+    const float* src = (second ? pb : pa) + (size_t)cloud * n * 3;
+    float4* dst = (second ? ob : oa) + (size_t)cloud * n;
+    uint16_t* cs = (second ? csb : csa) + (size_t)cloud * CS_STRIDE;
+    GridHdr* hdr = (second ? hb : ha) + cloud;
+    const int ncell = G * G * G;
+
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const float v = src[3 * (size_t)i + d];
+            lo[d] = fminf(lo[d], v); hi[d] = fmaxf(hi[d], v);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+            hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+        }
+        if (lane_id() == 0) { s_red[warp_id()][d] = lo[d]; s_red[warp_id()][3 + d] = hi[d]; }
+    }
+    for (int i = threadIdx.x; i < ncell; i += blockDim.x) counts[i] = 0;
+    __syncthreads();
+    float inv[3], hsum = 0.f;
+    int hdims = 0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        for (int w = 0; w < 32; ++w) { lo[d] = fminf(lo[d], s_red[w][d]); hi[d] = fmaxf(hi[d], s_red[w][3 + d]); }
+        const float ext = hi[d] - lo[d];
+        inv[d] = (ext > 0.f && ext < FLT_MAX) ? (float)G / ext : 0.f;
+        if (inv[d] > 0.f) { hsum += ext / (float)G; ++hdims; }
+    }
+    auto cell = [&](int i) {
+        const int cx = cell_of(src[3 * (size_t)i], lo[0], inv[0], G);
+        const int cy = cell_of(src[3 * (size_t)i + 1], lo[1], inv[1], G);
+        const int cz = cell_of(src[3 * (size_t)i + 2], lo[2], inv[2], G);
+        return (cz * G + cy) * G + cx;
+    };
+    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&counts[cell(i)], 1);
+    __syncthreads();
+    const int per = (ncell + (int)blockDim.x - 1) / (int)blockDim.x;
+    const int c0 = min(ncell, (int)threadIdx.x * per), c1 = min(ncell, c0 + per);
+    int local = 0, occupied = 0;
+    for (int c = c0; c < c1; ++c) { local += counts[c]; occupied += counts[c] > 0; }
+    int total;
+    int run = block_exclusive_scan(local, s_scan, &total);
+    for (int c = c0; c < c1; ++c) {
+        const int v = counts[c];
+        counts[c] = run;
+        cs[c] = (uint16_t)run;
+        run += v;
+    }
+    __shared__ int s_occ[33];
+    occupied = block_sum<int>(occupied, s_occ);
+    if (threadIdx.x == 0) {
+        cs[ncell] = (uint16_t)n;
+        GridHdr h;
+        const float hmean = hdims ? hsum / (float)hdims : 0.f;
+        h.r0 = fmaxf(0.5f * hmean * r0_scale * sqrtf((float)max(occupied, 1) / (float)max(n, 1)), 1e-20f);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { h.lo[d] = lo[d]; h.inv[d] = inv[d]; }
+        h.G = G;
+        *hdr = h;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int pos = atomicAdd(&counts[cell(i)], 1);
+        dst[pos] = make_float4(src[3 * (size_t)i], src[3 * (size_t)i + 1], src[3 * (size_t)i + 2], __int_as_float(i));
+    }
+}
+
+constexpr int GRID_QPW = 4;   // queries per warp (amortises the grid header)
+constexpr int GRID_CH = 3;    // candidate rounds (32 each) gathered per selection
+
+__device__ __forceinline__ bool key_less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
+// orders two (distance, index) keys so that a <= b
+__device__ __forceinline__ void key_sort2(float& da, int& ia, float& db, int& ib) {
+    const bool sw = key_less(db, ib, da, ia);
+    const float td = sw ? db : da;
+    const int ti = sw ? ib : ia;
+    db = sw ? da : db; ib = sw ? ia : ib;
+    da = td; ia = ti;
+}
+
+// One WARP per query (GRID_QPW consecutive queries per warp), so nothing diverges and candidate loads are coalesced runs:
+//   * lane = row of the cell box: loads the row's [start, end) from the cell offsets; a warp scan turns the row lengths
+//     into one flat candidate numbering;
+//   * lane = candidate: binary search (shuffles) for its row, one float4 load, exact (p - q)^2 distance, dropped unless it
+//     beats the current k-th key;
+//   * selection: each lane sorts its <= GRID_CH new keys + its slot of the running list, then the K smallest keys of the
+//     warp are extracted with two redux.sync.min per key (distance bits, then index among the ties); list slot s lives in
+//     lane s.
+// A pass is final when K keys were found and the k-th distance is <= r^2; otherwise r grows to that distance (or doubles)
+// and the search restarts with the old k-th distance as a filter.  grid: (ceil(P / (4 * GRID_QPW)), B).
+template <int K>
+__global__ void __launch_bounds__(GRID_THREADS) k_nn_grid(const float4* __restrict__ a, const float4* __restrict__ b,
+                                                          const uint16_t* __restrict__ cs_b, const GridHdr* __restrict__ hdr_b,
+                                                          int P, int Q, float* __restrict__ min_d, int32_t* __restrict__ min_i,
+                                                          int32_t* __restrict__ knn, int k_out) {
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int NONE = 0x7fffffff;
+    const int batch = blockIdx.y;
+    const int lane = lane_id();
+    const int wq0 = (blockIdx.x * (GRID_THREADS / 32) + warp_id()) * GRID_QPW;
+    if (wq0 >= P) return;
+    const GridHdr h = hdr_b[batch];
+    const int G = h.G;
+    const uint16_t* __restrict__ cs = cs_b + (size_t)batch * CS_STRIDE;
+    const float4* __restrict__ bq = b + (size_t)batch * Q;
+    for (int u = 0; u < GRID_QPW; ++u) {
+        const int qi = wq0 + u;
+        if (qi >= P) break;
+        const float4 ap = a[(size_t)batch * P + qi];
+        float ld = FLT_MAX;      // running list: slot `lane` (ascending over lanes 0..K-1)
+        int li = NONE;
+        float thr_d = FLT_MAX;   // only keys below (thr_d, thr_i) can still enter the list
+        int thr_i = NONE;
+        float r = h.r0;
+        for (int pass = 0; pass < 512; ++pass) {
+            const float rr = fmaf(r, 1e-5f, r) + 1e-30f;
+            const int x0 = cell_of(ap.x - rr, h.lo[0], h.inv[0], G), x1 = cell_of(ap.x + rr, h.lo[0], h.inv[0], G);
+            const int y0 = cell_of(ap.y - rr, h.lo[1], h.inv[1], G), y1 = cell_of(ap.y + rr, h.lo[1], h.inv[1], G);
+            const int z0 = cell_of(ap.z - rr, h.lo[2], h.inv[2], G), z1 = cell_of(ap.z + rr, h.lo[2], h.inv[2], G);
+            const int ny = y1 - y0 + 1, nrow = ny * (z1 - z0 + 1);
+            const float inv_ny = 1.0f / (float)ny;
+            ld = FLT_MAX; li = NONE;
+            for (int rbase = 0; rbase < nrow; rbase += 32) {
+                int s = 0, cnt = 0;
+                if (rbase + lane < nrow) {
+                    const int rz = (int)(((float)(rbase + lane) + 0.5f) * inv_ny), ry = (rbase + lane) - rz * ny;   // exact: < 2^10 rows
+                    const int row = ((z0 + rz) * G + (y0 + ry)) * G;
+                    s = cs[row + x0];
+                    cnt = (int)cs[row + x1 + 1] - s;
+                }
+                const int incl = warp_inclusive_scan(cnt);
+                const int m = __shfl_sync(FULL, incl, 31);
+                const int shift = s - (incl - cnt);                // candidate t of this row sits at bq[t + shift]
+                for (int base = 0; base < m; base += 32 * GRID_CH) {
+                    float vd[GRID_CH + 1];
+                    int vi[GRID_CH + 1];
+                    bool fresh = false;
+#pragma unroll
+                    for (int c = 0; c < GRID_CH; ++c) {
+                        vd[c] = FLT_MAX; vi[c] = NONE;
+                        if (base + c * 32 >= m) continue;           // warp-uniform: round not needed
+                        const int t = base + c * 32 + lane;
+                        int pos = 0;                                // number of rows that end at or before t
+#pragma unroll
+                        for (int step = 16; step > 0; step >>= 1) {
+                            const int v = __shfl_sync(FULL, incl, pos + step - 1);
+                            if (v <= t) pos += step;
+                        }
+                        const int sh = __shfl_sync(FULL, shift, pos);
+                        if (t < m) {
+                            const float4 cp = bq[t + sh];
+                            const float dx = ap.x - cp.x, dy = ap.y - cp.y, dz = ap.z - cp.z;
+                            const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                            const int ci = __float_as_int(cp.w);
+                            if (key_less(d, ci, thr_d, thr_i)) { vd[c] = d; vi[c] = ci; fresh = true; }
+                        }
+                    }
+                    if (!__any_sync(FULL, fresh)) continue;
+                    vd[GRID_CH] = ld; vi[GRID_CH] = li;
+                    static_assert(GRID_CH == 3, "sorting network below is for 4 keys");
+                    key_sort2(vd[0], vi[0], vd[1], vi[1]);
+                    key_sort2(vd[2], vi[2], vd[3], vi[3]);
+                    key_sort2(vd[0], vi[0], vd[2], vi[2]);
+                    key_sort2(vd[1], vi[1], vd[3], vi[3]);
+                    key_sort2(vd[1], vi[1], vd[2], vi[2]);
+                    ld = FLT_MAX; li = NONE;
+#pragma unroll
+                    for (int sidx = 0; sidx < K; ++sidx) {
+                        const unsigned fb = __float_as_uint(vd[0]);
+                        const unsigned mn = __reduce_min_sync(FULL, fb);
+                        const unsigned mi = __reduce_min_sync(FULL, fb == mn ? (unsigned)vi[0] : 0xffffffffu);
+                        if (lane == sidx) { ld = __uint_as_float(mn); li = (int)mi; }
+                        if (fb == mn && (unsigned)vi[0] == mi) {
+#pragma unroll
+                            for (int c = 0; c < GRID_CH; ++c) { vd[c] = vd[c + 1]; vi[c] = vi[c + 1]; }
+                            vd[GRID_CH] = FLT_MAX; vi[GRID_CH] = NONE;
+                        }
+                    }
+                    const float kd = __shfl_sync(FULL, ld, K - 1);
+                    const int ki = __shfl_sync(FULL, li, K - 1);
+                    if (ki != NONE) { thr_d = kd; thr_i = ki; }
+                }
+            }
+            const float kd = __shfl_sync(FULL, ld, K - 1);
+            const bool full = __shfl_sync(FULL, li, K - 1) != NONE;
+            if (full && kd <= r * r) break;
+            const bool all = (h.inv[0] == 0.f || (x0 == 0 && x1 == G - 1)) && (h.inv[1] == 0.f || (y0 == 0 && y1 == G - 1)) &&
+                             (h.inv[2] == 0.f || (z0 == 0 && z1 == G - 1));
+            if (all) break;
+            if (full) {
+                r = fmaf(sqrtf(kd), 1e-6f, sqrtf(kd));
+                thr_d = kd; thr_i = NONE;                           // restart: every key with d <= kd is admitted again
+            } else {
+                r = 2.f * r;
+            }
+        }
+        const size_t o = (size_t)batch * P + __float_as_int(ap.w);
+        if (lane == 0) { min_d[o] = ld; min_i[o] = li; }
+        if (lane < k_out) knn[o * k_out + lane] = li;
+    }
+}
+
 // sum of a float array into a double accumulator (atomic per block)
 __global__ void __launch_bounds__(256) k_sum(const float* __restrict__ x, long long n, double* __restrict__ out) {
     __shared__ double sd[33];
@@ -391,15 +651,41 @@ static bool pack_cloud(const float* pts, int B, int P, float4* out, float2* tran
 using namespace mrb;
 using namespace mrb::chamfer;
 
+namespace {
+struct Workspace {
+    float4 *pa, *pb;
+    float2 *tra, *trb;
+    GridHdr *ha, *hb;
+    uint16_t *csa, *csb;
+    long long bytes;
+};
+// carves the caller's workspace; with base == 0 only the size is computed
+Workspace carve(uintptr_t base, int B, int P, int Q) {
+    Workspace w;
+    uintptr_t p = (base + 15) & ~(uintptr_t)15;
+    w.pa = reinterpret_cast<float4*>(p); p += sizeof(float4) * (size_t)B * P;
+    w.pb = reinterpret_cast<float4*>(p); p += sizeof(float4) * (size_t)B * Q;
+    w.tra = reinterpret_cast<float2*>(p); p += sizeof(float2) * (size_t)B * ceil_div(max(P, 1), TILE);
+    w.trb = reinterpret_cast<float2*>(p); p += sizeof(float2) * (size_t)B * ceil_div(max(Q, 1), TILE);
+    p = (p + 15) & ~(uintptr_t)15;
+    w.ha = reinterpret_cast<GridHdr*>(p); p += sizeof(GridHdr) * (size_t)B;
+    w.hb = reinterpret_cast<GridHdr*>(p); p += sizeof(GridHdr) * (size_t)B;
+    w.csa = reinterpret_cast<uint16_t*>(p); p += sizeof(uint16_t) * (size_t)B * CS_STRIDE;
+    w.csb = reinterpret_cast<uint16_t*>(p); p += sizeof(uint16_t) * (size_t)B * CS_STRIDE;
+    w.bytes = (long long)(p - base) + 16;
+    return w;
+}
+}  // namespace
+
 extern "C" long long mrb_knn_workspace_bytes(int B, int P, int Q) {
     if (B < 0 || P < 0 || Q < 0) return -1;
-    const long long tiles = (long long)B * (ceil_div(max(P, 1), TILE) + ceil_div(max(Q, 1), TILE));
-    return (long long)sizeof(float4) * ((long long)B * P + (long long)B * Q) + (long long)sizeof(float2) * tiles + 256;
+    return carve(0, B, P, Q).bytes;
 }
 
-extern "C" int mrb_knn_fwd(const float* a, const float* b, int B, int P, int Q, int k, float* min_d_a, int32_t* min_i_a,
-                           int32_t* knn_a, float* min_d_b, int32_t* min_i_b, int32_t* knn_b, void* workspace,
-                           void* stream_) {
+// algo: 0 = automatic (cell grid when both clouds have <= 65535 points, else the tiled scan), 1 = tiled scan, 2 = cell grid
+extern "C" int mrb_knn_fwd_algo(const float* a, const float* b, int B, int P, int Q, int k, float* min_d_a, int32_t* min_i_a,
+                                int32_t* knn_a, float* min_d_b, int32_t* min_i_b, int32_t* knn_b, void* workspace, int algo,
+                                void* stream_) {
     MRB_REQUIRE(a && b && workspace, "knn_fwd: null pointer");
     MRB_REQUIRE(k >= 0 && k <= 16, "knn_fwd: k must be in [0, 16], got %d", k);
     MRB_REQUIRE((min_d_a && min_i_a) || (min_d_b && min_i_b), "knn_fwd: no output requested");
@@ -407,18 +693,44 @@ extern "C" int mrb_knn_fwd(const float* a, const float* b, int B, int P, int Q, 
     MRB_REQUIRE(k <= Q && k <= P, "knn_fwd: k = %d exceeds a cloud size (%d, %d)", k, P, Q);
     MRB_REQUIRE(B == 0 || (P > 0 && Q > 0), "knn_fwd: empty cloud");
     MRB_REQUIRE(B <= 65535, "knn_fwd: batch too large");
+    MRB_REQUIRE(algo >= 0 && algo <= 2, "knn_fwd: unknown algo %d", algo);
+    const bool grid_ok = P <= GRID_MAX_POINTS && Q <= GRID_MAX_POINTS;
+    MRB_REQUIRE(algo != 2 || grid_ok, "knn_fwd: the cell-grid path holds at most %d points per cloud", GRID_MAX_POINTS);
     if (B == 0) return MRB_OK;
     cudaStream_t s = (cudaStream_t)stream_;
-    float4* pa = reinterpret_cast<float4*>(((uintptr_t)workspace + 15) & ~(uintptr_t)15);
-    float4* pb = pa + (size_t)B * P;
-    float2* tra = reinterpret_cast<float2*>(pb + (size_t)B * Q);
-    float2* trb = tra + (size_t)B * ceil_div(P, TILE);
-    const bool sa = pack_cloud(a, B, P, pa, tra, s);
-    const bool sb = pack_cloud(b, B, Q, pb, trb, s);
+    const Workspace w = carve((uintptr_t)workspace, B, P, Q);
+    if (algo == 2 || (algo == 0 && grid_ok)) {
+        const int Ga = grid_cells(P), Gb = grid_cells(Q);
+        const int G = max(Ga, Gb);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_grid_build, cudaFuncAttributeMaxDynamicSharedMemorySize, GMAX * GMAX * GMAX * 4);
+            attr_set = true;
+        }
+        k_grid_build<<<2 * B, 1024, (size_t)G * G * G * 4, s>>>(a, b, B, P, Q, Ga, Gb, w.pa, w.pb, w.csa, w.csb, w.ha, w.hb,
+                                                                sqrtf(GRID_C0 * (float)max(k, 1)));
+#define MRB_NNG(KK)                                                                                                   \
+    do {                                                                                                              \
+        if (min_d_a)                                                                                                  \
+            k_nn_grid<KK><<<dim3(ceil_div(P, (GRID_THREADS / 32) * GRID_QPW), B), GRID_THREADS, 0, s>>>(w.pa, w.pb, w.csb, w.hb, P, Q, min_d_a, \
+                                                                                      min_i_a, knn_a, k);             \
+        if (min_d_b)                                                                                                  \
+            k_nn_grid<KK><<<dim3(ceil_div(Q, (GRID_THREADS / 32) * GRID_QPW), B), GRID_THREADS, 0, s>>>(w.pb, w.pa, w.csa, w.ha, Q, P, min_d_b, \
+                                                                                      min_i_b, knn_b, k);             \
+    } while (0)
+        if (k <= 1) MRB_NNG(1);
+        else if (k <= 4) MRB_NNG(4);
+        else if (k <= 10) MRB_NNG(10);
+        else MRB_NNG(16);
+#undef MRB_NNG
+        return check_launch("knn_fwd (grid)");
+    }
+    const bool sa = pack_cloud(a, B, P, w.pa, w.tra, s);
+    const bool sb = pack_cloud(b, B, Q, w.pb, w.trb, s);
 #define MRB_NN(KK)                                                                                        \
     do {                                                                                                  \
-        if (min_d_a) launch_nn<KK>(pa, pb, trb, B, P, Q, sb ? 1 : 0, min_d_a, min_i_a, knn_a, k, s);      \
-        if (min_d_b) launch_nn<KK>(pb, pa, tra, B, Q, P, sa ? 1 : 0, min_d_b, min_i_b, knn_b, k, s);      \
+        if (min_d_a) launch_nn<KK>(w.pa, w.pb, w.trb, B, P, Q, sb ? 1 : 0, min_d_a, min_i_a, knn_a, k, s);  \
+        if (min_d_b) launch_nn<KK>(w.pb, w.pa, w.tra, B, Q, P, sa ? 1 : 0, min_d_b, min_i_b, knn_b, k, s);  \
     } while (0)
     if (k <= 1) MRB_NN(1);
     else if (k <= 4) MRB_NN(4);
@@ -426,6 +738,12 @@ extern "C" int mrb_knn_fwd(const float* a, const float* b, int B, int P, int Q, 
     else MRB_NN(16);
 #undef MRB_NN
     return check_launch("knn_fwd");
+}
+
+extern "C" int mrb_knn_fwd(const float* a, const float* b, int B, int P, int Q, int k, float* min_d_a, int32_t* min_i_a,
+                           int32_t* knn_a, float* min_d_b, int32_t* min_i_b, int32_t* knn_b, void* workspace,
+                           void* stream_) {
+    return mrb_knn_fwd_algo(a, b, B, P, Q, k, min_d_a, min_i_a, knn_a, min_d_b, min_i_b, knn_b, workspace, 0, stream_);
 }
 
 extern "C" int mrb_sum_scaled(const float* x, long long n, double scale, double* acc, float* out, void* stream_) {

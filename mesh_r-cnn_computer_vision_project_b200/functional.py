@@ -467,6 +467,36 @@ def sample_points(verts: Tensor, faces: Tensor, v_index: Sequence[int], f_index:
                          max(f_index) if B else 0, int(n), u, face_idx, xi2, xi1, seed)
 
 
+KNN_ALGOS = {"auto": 0, "tiled": 1, "grid": 2}
+
+
+def knn_search(p: Tensor, q: Tensor, k: int = 0, algo: str = "auto"):
+    """Exact nearest / k-nearest neighbours in both directions between B x P x 3 and B x Q x 3 clouds (no gradient):
+    (d_p, i_p, knn_p, d_q, i_q, knn_q) -- squared distance and int32 index of the nearest point of the other cloud and
+    the k nearest indices sorted by (distance, index) (None when k = 0).  ``algo``: "auto" | "tiled" | "grid"
+    (mrb_knn_fwd_algo; both strategies return identical results)."""
+    _require_cuda(p, "knn_search")
+    _require_cuda(q, "knn_search")
+    pc, qc = _f32c(p.detach()), _f32c(q.detach())
+    B, P, _ = pc.shape
+    Q = qc.shape[1]
+    dev = p.device
+    dp = torch.empty(B, P, dtype=torch.float32, device=dev)
+    dq = torch.empty(B, Q, dtype=torch.float32, device=dev)
+    ip = torch.empty(B, P, dtype=torch.int32, device=dev)
+    iq = torch.empty(B, Q, dtype=torch.int32, device=dev)
+    kp = torch.empty(B, P, k, dtype=torch.int32, device=dev) if k else None
+    kq = torch.empty(B, Q, k, dtype=torch.int32, device=dev) if k else None
+    ws = torch.empty(_lib.load().mrb_knn_workspace_bytes(B, P, Q), dtype=torch.uint8, device=dev)
+    args = (_lib.ptr(pc), _lib.ptr(qc), B, P, Q, k, _lib.ptr(dp), _lib.ptr(ip), _lib.ptr(kp), _lib.ptr(dq), _lib.ptr(iq),
+            _lib.ptr(kq), _lib.ptr(ws))
+    if algo == "auto":
+        _lib.call("mrb_knn_fwd", *args)
+    else:
+        _lib.call("mrb_knn_fwd_algo", *args, KNN_ALGOS[algo])
+    return dp, ip, kp, dq, iq, kq
+
+
 class _Chamfer(torch.autograd.Function):
     """Both directions of the nearest-neighbour search (+ optional k-NN index sets) and the two chamfer sums."""
 
@@ -478,15 +508,7 @@ class _Chamfer(torch.autograd.Function):
         B, P, _ = pc.shape
         Q = qc.shape[1]
         dev = p.device
-        dp = torch.empty(B, P, dtype=torch.float32, device=dev)
-        dq = torch.empty(B, Q, dtype=torch.float32, device=dev)
-        ip = torch.empty(B, P, dtype=torch.int32, device=dev)
-        iq = torch.empty(B, Q, dtype=torch.int32, device=dev)
-        kp = torch.empty(B, P, k, dtype=torch.int32, device=dev) if k else None
-        kq = torch.empty(B, Q, k, dtype=torch.int32, device=dev) if k else None
-        ws = torch.empty(_lib.load().mrb_knn_workspace_bytes(B, P, Q), dtype=torch.uint8, device=dev)
-        _lib.call("mrb_knn_fwd", _lib.ptr(pc), _lib.ptr(qc), B, P, Q, k, _lib.ptr(dp), _lib.ptr(ip), _lib.ptr(kp),
-                  _lib.ptr(dq), _lib.ptr(iq), _lib.ptr(kq), _lib.ptr(ws))
+        dp, ip, kp, dq, iq, kq = knn_search(pc, qc, k)
         acc = torch.empty(2, dtype=torch.float64, device=dev)
         sums = torch.empty(2, dtype=torch.float32, device=dev)
         _lib.call("mrb_sum_scaled", _lib.ptr(dp), B * P, 1.0, _lib.ptr(acc), _lib.ptr(sums))

@@ -20,9 +20,10 @@ kp = torch.empty(B, P, max(k, 1), dtype=torch.int32, device=dev)
 dq = torch.empty(B, P, device=dev); iq = torch.empty(B, P, dtype=torch.int32, device=dev)
 kq = torch.empty(B, P, max(k, 1), dtype=torch.int32, device=dev)
 ws = torch.empty(_lib.load().mrb_knn_workspace_bytes(B, P, P), dtype=torch.uint8, device=dev)
+algo = int(sys.argv[2]) if len(sys.argv) > 2 else 0        # 0 auto, 1 tiled scan, 2 cell grid
 def run():
-    _lib.call("mrb_knn_fwd", _lib.ptr(p), _lib.ptr(q), B, P, P, k, _lib.ptr(dp), _lib.ptr(ip), _lib.ptr(kp),
-              _lib.ptr(dq), _lib.ptr(iq), _lib.ptr(kq), _lib.ptr(ws))
+    _lib.call("mrb_knn_fwd_algo", _lib.ptr(p), _lib.ptr(q), B, P, P, k, _lib.ptr(dp), _lib.ptr(ip), _lib.ptr(kp),
+              _lib.ptr(dq), _lib.ptr(iq), _lib.ptr(kq), _lib.ptr(ws), algo)
 for _ in range(3): run()
 torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -31,4 +32,4 @@ a.record()
 for _ in range(n): run()
 b.record(); torch.cuda.synchronize()
 ms = a.elapsed_time(b) / n
-print("k=%d  %.3f ms/call (both directions)  %.3f Tpairs/s  mean NN d^2 = %.4f" % (k, ms, 2 * B * P * P / ms / 1e9, float(dp.mean())))
+print("algo=%d k=%d  %.3f ms/call (both directions)  %.3f Tpairs/s  mean NN d^2 = %.4f" % (algo, k, ms, 2 * B * P * P / ms / 1e9, float(dp.mean())))

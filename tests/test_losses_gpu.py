@@ -120,6 +120,8 @@ def test_knn_ragged_sizes_vs_oracle(lib, B, P, Q, k):
     gen = torch.Generator().manual_seed(B * 1000 + P)
     p, q = torch.rand(B, P, 3, generator=gen) - 0.5, torch.rand(B, Q, 3, generator=gen) - 0.5
     l1, l2, ip, iq, kp, kq = F_.chamfer_knn(p.cuda(), q.cuda(), k)
+    _, ip_t, kp_t, _, iq_t, kq_t = F_.knn_search(p.cuda(), q.cuda(), k, algo="tiled")
+    assert torch.equal(ip, ip_t) and torch.equal(iq, iq_t) and (not k or (torch.equal(kp, kp_t) and torch.equal(kq, kq_t)))
     d = mesh_ops.p2p_distance(p.double(), q.double())
     w1, wi1, w2, wi2 = mesh_ops.chamfer(d)
     close(l1, w1, what="l1")
@@ -129,6 +131,53 @@ def test_knn_ragged_sizes_vs_oracle(lib, B, P, Q, k):
         for got, dd in ((kp, d), (kq, d.transpose(1, 2))):
             want = dd.topk(k, dim=2, largest=False).indices.sort(-1).values
             assert torch.equal(got.cpu().long().sort(-1).values, want)
+
+
+def _knn_clouds(kind, B, P, Q, seed):
+    gen = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.rand(*s, generator=gen)
+    if kind == "cube":
+        return r(B, P, 3) - 0.5, r(B, Q, 3) - 0.5
+    if kind == "sphere":                                   # points on two different surfaces
+        a, b = torch.randn(B, P, 3, generator=gen), torch.randn(B, Q, 3, generator=gen)
+        return a / a.norm(dim=2, keepdim=True), 0.7 * b / b.norm(dim=2, keepdim=True) * torch.tensor([1.0, 0.6, 1.4])
+    if kind == "far":                                      # queries far outside the other cloud's bounding box
+        return r(B, P, 3) + 5.0, r(B, Q, 3) * 0.1
+    if kind == "plane":                                    # degenerate axis (z extent 0) and an x-y lattice full of ties
+        a = torch.stack([torch.randint(0, 12, (B, P), generator=gen).float(),
+                         torch.randint(0, 12, (B, P), generator=gen).float(), torch.zeros(B, P)], 2)
+        b = torch.stack([torch.randint(0, 12, (B, Q), generator=gen).float(),
+                         torch.randint(0, 12, (B, Q), generator=gen).float(), torch.zeros(B, Q)], 2)
+        return a, b
+    if kind == "point":                                    # every candidate identical
+        return r(B, P, 3), torch.full((B, Q, 3), 0.25)
+    if kind == "clusters":                                 # two tight clusters far apart: most cells empty
+        a = torch.where(r(B, P, 1) < 0.5, r(B, P, 3) * 1e-3, r(B, P, 3) * 1e-3 + 10.0)
+        b = torch.where(r(B, Q, 1) < 0.1, r(B, Q, 3) * 1e-3, r(B, Q, 3) * 1e-3 + 10.0)
+        return a, b
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind,B,P,Q,k", [
+    ("cube", 2, 3000, 2500, 10), ("sphere", 2, 10000, 10000, 10), ("far", 1, 500, 700, 4), ("plane", 2, 900, 1100, 10),
+    ("point", 1, 300, 200, 16), ("clusters", 2, 2000, 2000, 10), ("cube", 3, 17, 16, 16), ("sphere", 1, 4000, 9000, 1),
+    ("cube", 1, 1, 1, 1), ("cube", 2, 2000, 3000, 0)])
+def test_knn_grid_equals_tiled_scan(lib, kind, B, P, Q, k):
+    """The cell-grid search and the tiled brute-force scan must agree bit for bit (distances, nearest index, and the
+    ordered k-NN lists incl. (distance, index) tie-breaking); the tiled scan is itself checked against the oracle."""
+    from meshrcnn_b200 import functional as F_
+    p, q = _knn_clouds(kind, B, P, Q, seed=P + Q + k)
+    got = F_.knn_search(p.cuda(), q.cuda(), k, algo="grid")
+    want = F_.knn_search(p.cuda(), q.cuda(), k, algo="tiled")
+    for name, a, b in zip(("d_p", "i_p", "knn_p", "d_q", "i_q", "knn_q"), got, want):
+        if a is None:
+            assert b is None
+            continue
+        assert torch.equal(a, b), "%s differs on %s: %d of %d" % (name, kind, int((a != b).sum()), a.numel())
+    # and against exact fp64 distances (ties broken by index, like torch.min on the oracle's matrix)
+    d = mesh_ops.p2p_distance(p.double(), q.double())
+    dd = torch.gather(d, 2, got[1].long().cpu().unsqueeze(2)).squeeze(2)
+    assert torch.allclose(dd, d.min(dim=2).values, rtol=1e-5, atol=1e-12)
 
 
 def test_mesh_loss_matches_reference(lib, golden):
