@@ -11,7 +11,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmeshrcnn_b200.so")
+LIB_PATH = os.environ.get("MRB_LIB_PATH") or os.path.join(_HERE, "libmeshrcnn_b200.so")   # override: diagnostic builds
 
 _C = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_longlong, "L": ctypes.c_ulonglong, "f": ctypes.c_float,
       "d": ctypes.c_double}

@@ -20,6 +20,7 @@
 //               epilogue; the whole warp owns the TMEM allocation
 //   warp 17     lane 0 streams the packed weight chunk with cp.async.bulk (TMA bulk copy) onto the stage's mbarrier
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/meshrcnn_b200.h"
 
 namespace mrb {
@@ -94,6 +95,19 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// 32 lanes x 32 consecutive fp32 columns of TMEM -> 32 registers per thread (thread = lane / row, register = column)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]),
+          "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]),
+          "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+
 struct Params {
     const float* A;
     int lda, M, K;
@@ -103,6 +117,7 @@ struct Params {
     int acc_bufs;                    // 2: the epilogue of tile j overlaps the MMAs of tile j+1 (double-buffered TMEM)
     int mtiles, ntiles;
     int accumulate;                  // epilogue adds to C (K is processed in segments, see mrb_gemm_tc)
+    int stages, stage_bytes;         // shared-memory ring: stages x (A hi | A lo | B hi | B lo)
     long long img_tile_stride;       // bytes between the images of consecutive N tiles
     float* C;
     int ldc;
@@ -110,26 +125,34 @@ struct Params {
 
 constexpr int PROD_WARPS = 8;        // A producer warps, 16 rows of the 128-row tile each
 constexpr int PROD_ROWS = BM / PROD_WARPS;
-constexpr int PREFETCH = 2;          // A chunks in flight per producer thread (registers)
+#ifndef MRB_TC_PREFETCH
+#define MRB_TC_PREFETCH 2
+#endif
+constexpr int PREFETCH = MRB_TC_PREFETCH;   // A chunks in flight per producer thread (registers)
+// Diagnostic builds (scripts/gemm_variants.sh): -DMRB_DIAG_NOLOAD (producers skip the global loads), -DMRB_DIAG_NOMMA (the
+// issuer skips the MMAs), -DMRB_DIAG_NOSTORE (the epilogue skips the C stores) isolate the three legs of the pipeline.
 constexpr int EPI_WARPS = 8;         // epilogue warps: TMEM lane quadrant = warp % 4, column half = (warp - PROD_WARPS) / 4
 constexpr int TC_THREADS = (PROD_WARPS + EPI_WARPS + 2) * 32;   // producers | epilogue warps | MMA issuer | weight TMA
 constexpr int EPI_BYTES = EPI_WARPS * 32 * 33 * 4;
-constexpr int TC_SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
+constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_SMEM_LIMIT = 232448;                                    // 227 KB opt-in maximum per CTA
+constexpr int TC_RING_BYTES = TC_SMEM_LIMIT - EPI_BYTES - 1024 - 256;   // what the stage ring may use
 
 // Persistent: grid = min(#tiles, #SMs); every role loops over the CTA's tiles with pipeline state that carries across
 // tiles, so global-load latency, tensor work and the C write-back of consecutive tiles overlap on one SM.
 __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int STAGES = p.stages, STAGE_BYTES = p.stage_bytes;
     float* epi = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);   // full[2] empty[2] tfull[2] tempty[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_BYTES);   // full[4] empty[4] tfull[2] tempty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t bar_base = smem_u32(bars);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
-    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (TC_MAX_STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * TC_MAX_STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * TC_MAX_STAGES + 2 + a); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NT = p.NT;
@@ -141,12 +164,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full_bar(s), PROD_WARPS * 32 + 1);
+            mbar_init(full_bar(s), PROD_WARPS + 1);     // one elected arrive per producer warp + the weight TMA's expect_tx
             mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), EPI_WARPS * 32);
+            mbar_init(tempty_bar(a), EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -167,42 +190,108 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
         // PREFETCH chunks (16 coalesced 128-byte row segments each) outstanding in registers, across tile boundaries.
         const int r0 = warp * PROD_ROWS;
         const int total_its = my_tiles * p.nchunks;
-        float v[PREFETCH][PROD_ROWS];
-        auto load_it = [&](int it, float (&dst)[PROD_ROWS]) {
-            const int tile = blockIdx.x + (it / p.nchunks) * gridDim.x;
-            const int c = it % p.nchunks;
-            const int m0 = (tile / p.ntiles) * BM;
-            const int k = c * BK + lane;
-            const bool kin = k < p.K;
+        if (((p.lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0)) {
+            // 16-byte aligned rows: lane = (row r0 + 4 i + lane / 8, 16-byte k chunk lane % 8) -> 4 x ld.global.v4 and
+            // 8 x st.shared.v4 per chunk instead of 16 + 32 scalar accesses (4x fewer requests in the L1 miss queue, which
+            // is what bounds the scalar path); a quarter-warp writes one complete swizzled 128-byte row (conflict free).
+            const int rsub = lane >> 3, kc = lane & 7;
+            float4 v[PREFETCH][PROD_ROWS / 4];
+            auto load_it = [&](int it, float4 (&dst)[PROD_ROWS / 4]) {
+                const int tile = blockIdx.x + (it / p.nchunks) * gridDim.x;
+                const int c = it % p.nchunks;
+                const int m0 = (tile / p.ntiles) * BM;
+                // Always-valid (clamped) addresses and NO use of the loaded value here: masking happens at store time, so the
+                // loads of PREFETCH chunks really stay in flight (a select on the loaded value would wait for it right away).
+                const int k = min(c * BK + kc * 4, p.lda - 4);
 #pragma unroll
-            for (int i = 0; i < PROD_ROWS; ++i) {
-                const int gm = m0 + r0 + i;
-                dst[i] = (kin && gm < p.M) ? __ldg(p.A + (size_t)gm * p.lda + k) : 0.f;
-            }
-        };
+                for (int i = 0; i < PROD_ROWS / 4; ++i) {
+                    const int gm = min(m0 + r0 + 4 * i + rsub, p.M - 1);
+#ifdef MRB_DIAG_NOLOAD
+                    dst[i] = make_float4((float)gm, (float)k, 1.f, 2.f);
+#else
+                    dst[i] = __ldg(reinterpret_cast<const float4*>(p.A + (size_t)gm * p.lda + k));
+#endif
+                }
+            };
 #pragma unroll
-        for (int d = 0; d < PREFETCH; ++d)
-            if (d < total_its) load_it(d, v[d]);
-        for (int it0 = 0; it0 < total_its; it0 += PREFETCH) {
+            for (int d = 0; d < PREFETCH; ++d)
+                if (d < total_its) load_it(d, v[d]);
+            for (int it0 = 0; it0 < total_its; it0 += PREFETCH) {
 #pragma unroll
-            for (int d = 0; d < PREFETCH; ++d) {
-                const int it = it0 + d;
-                if (it < total_its) {
-                    const int s = it % STAGES, use = it / STAGES;
-                    if (use > 0) mbar_wait(empty_bar(s), (use - 1) & 1);
-                    unsigned char* a_hi = smem + s * STAGE_BYTES;
-                    unsigned char* a_lo = a_hi + A_BYTES;
+                for (int d = 0; d < PREFETCH; ++d) {
+                    const int it = it0 + d;
+                    if (it < total_its) {
+                        const int s = it % STAGES, use = it / STAGES;
+                        if (use > 0) mbar_wait(empty_bar(s), (use - 1) & 1);
+                        unsigned char* a_hi = smem + s * STAGE_BYTES;
+                        unsigned char* a_lo = a_hi + A_BYTES;
+                        const int m0 = ((blockIdx.x + (it / p.nchunks) * gridDim.x) / p.ntiles) * BM;
+                        const int kleft = p.K - ((it % p.nchunks) * BK + kc * 4);   // valid columns of this 16-byte chunk
 #pragma unroll
-                    for (int i = 0; i < PROD_ROWS; ++i) {
-                        const float hi = tf32_rna(v[d][i]);
-                        const float lo = tf32_rna(v[d][i] - hi);
-                        const int off = swz(r0 + i, lane);
-                        *reinterpret_cast<float*>(a_hi + off) = hi;
-                        *reinterpret_cast<float*>(a_lo + off) = lo;
+                        for (int i = 0; i < PROD_ROWS / 4; ++i) {
+                            float4 x = v[d][i];
+                            const bool rin = m0 + r0 + 4 * i + rsub < p.M;
+                            x.x = (rin && kleft > 0) ? x.x : 0.f;       // columns [K, lda) of a row are padding (may hold anything)
+                            x.y = (rin && kleft > 1) ? x.y : 0.f;
+                            x.z = (rin && kleft > 2) ? x.z : 0.f;
+                            x.w = (rin && kleft > 3) ? x.w : 0.f;
+                            float4 hi, lo;
+                            hi.x = tf32_rna(x.x); hi.y = tf32_rna(x.y); hi.z = tf32_rna(x.z); hi.w = tf32_rna(x.w);
+                            lo.x = tf32_rna(x.x - hi.x); lo.y = tf32_rna(x.y - hi.y); lo.z = tf32_rna(x.z - hi.z);
+                            lo.w = tf32_rna(x.w - hi.w);
+                            const int row = r0 + 4 * i + rsub;
+                            const int off = (row >> 3) * 1024 + (row & 7) * 128 + (((kc ^ (row & 7)) & 7) << 4);
+                            *reinterpret_cast<float4*>(a_hi + off) = hi;
+                            *reinterpret_cast<float4*>(a_lo + off) = lo;
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(full_bar(s));
+                        if (it + PREFETCH < total_its) load_it(it + PREFETCH, v[d]);
                     }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA
-                    mbar_arrive(full_bar(s));
-                    if (it + PREFETCH < total_its) load_it(it + PREFETCH, v[d]);
+                }
+            }
+        } else {
+            float v[PREFETCH][PROD_ROWS];
+            auto load_it = [&](int it, float (&dst)[PROD_ROWS]) {
+                const int tile = blockIdx.x + (it / p.nchunks) * gridDim.x;
+                const int c = it % p.nchunks;
+                const int m0 = (tile / p.ntiles) * BM;
+                const int k = min(c * BK + lane, p.K - 1);      // clamped, masked at store time (see the vector path)
+#pragma unroll
+                for (int i = 0; i < PROD_ROWS; ++i) {
+                    const int gm = min(m0 + r0 + i, p.M - 1);
+                    dst[i] = __ldg(p.A + (size_t)gm * p.lda + k);
+                }
+            };
+#pragma unroll
+            for (int d = 0; d < PREFETCH; ++d)
+                if (d < total_its) load_it(d, v[d]);
+            for (int it0 = 0; it0 < total_its; it0 += PREFETCH) {
+#pragma unroll
+                for (int d = 0; d < PREFETCH; ++d) {
+                    const int it = it0 + d;
+                    if (it < total_its) {
+                        const int s = it % STAGES, use = it / STAGES;
+                        if (use > 0) mbar_wait(empty_bar(s), (use - 1) & 1);
+                        unsigned char* a_hi = smem + s * STAGE_BYTES;
+                        unsigned char* a_lo = a_hi + A_BYTES;
+                        const int m0 = ((blockIdx.x + (it / p.nchunks) * gridDim.x) / p.ntiles) * BM;
+                        const bool kin = (it % p.nchunks) * BK + lane < p.K;
+#pragma unroll
+                        for (int i = 0; i < PROD_ROWS; ++i) {
+                            const float x = (kin && m0 + r0 + i < p.M) ? v[d][i] : 0.f;
+                            const float hi = tf32_rna(x);
+                            const float lo = tf32_rna(x - hi);
+                            const int off = swz(r0 + i, lane);
+                            *reinterpret_cast<float*>(a_hi + off) = hi;
+                            *reinterpret_cast<float*>(a_lo + off) = lo;
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(full_bar(s));    // 256 per-thread arrives on one mbarrier serialise (~10 cycles each)
+                        if (it + PREFETCH < total_its) load_it(it + PREFETCH, v[d]);
+                    }
                 }
             }
         }
@@ -229,43 +318,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
             for (int blk = blk_beg; blk < blk_end; ++blk) {
                 const int c0 = blk * 32;
                 float acc[32];
-#pragma unroll
-                for (int q = 0; q < 32; ++q) acc[q] = 0.f;
-                for (int a = 0; a < p.nacc; ++a) {
-                    uint32_t v[32];
-                    const uint32_t taddr = tmem_d + ((uint32_t)(ew * 32) << 16) + (uint32_t)(a * p.tmem_cols + c0);
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
-                          "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
-                          "=r"(v[30]), "=r"(v[31])
-                        : "r"(taddr));
+                {
+                    // both accumulator reads are in flight before the single wait
+                    uint32_t v0[32], v1[32];
+                    const uint32_t taddr = tmem_d + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0;
+                    tmem_ld32(taddr, v0);
+                    tmem_ld32(taddr + (uint32_t)p.tmem_cols, v1);         // nacc >= 2 always (main + cross-term accumulator)
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) acc[q] += __uint_as_float(v[q]);
+                    for (int q = 0; q < 32; ++q) acc[q] = __uint_as_float(v0[q]) + __uint_as_float(v1[q]);
+                    for (int a = 2; a < p.nacc; ++a) {
+                        tmem_ld32(taddr + (uint32_t)(a * p.tmem_cols), v1);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) acc[q] += __uint_as_float(v1[q]);
+                    }
                 }
                 if (blk + 1 == blk_end) {
                     // last read of this accumulator by this warp: hand the TMEM buffer back before the stores
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    mbar_arrive(tempty_bar(ab));
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar(ab));
                 }
                 const int colbase = n0 + c0;
                 if (aligned && c0 + 32 <= NT && colbase + 32 <= p.N) {
-                    if (gm_mine < p.M) {
-                        float4* dst = reinterpret_cast<float4*>(p.C + (size_t)gm_mine * p.ldc + colbase);
-                        if (p.accumulate) {
+                    // Each thread holds 32 columns of ONE row; storing them directly would touch 32 different 128-byte lines
+                    // per instruction.  The block goes through a swizzled (conflict-free) shared-memory tile instead, so
+                    // that every st.global.v4 instruction writes four complete 128-byte row segments.
+                    float4* st4 = reinterpret_cast<float4*>(stage_t);          // 32 rows x 8 chunks of 16 bytes
+                    __syncwarp();
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const float4 o = dst[q];
-                                acc[4 * q] += o.x; acc[4 * q + 1] += o.y; acc[4 * q + 2] += o.z; acc[4 * q + 3] += o.w;
+                    for (int q = 0; q < 8; ++q)
+                        st4[lane * 8 + (q ^ (lane & 7))] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+                    __syncwarp();
+                    const int rsub = lane >> 3, ch = lane & 7;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int r = 4 * j + rsub;
+                        float4 o = st4[r * 8 + (ch ^ (r & 7))];
+                        const int gm = m0 + ew * 32 + r;
+                        if (gm < p.M) {
+                            float4* dst = reinterpret_cast<float4*>(p.C + (size_t)gm * p.ldc + colbase) + ch;
+                            if (p.accumulate) {
+                                const float4 old = *dst;
+                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
                             }
+#ifdef MRB_DIAG_NOSTORE
+                            if (o.x == 1.2345e-33f)
+#endif
+                            *dst = o;
                         }
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) dst[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
                     }
                 } else {
                     __syncwarp();
@@ -285,7 +387,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
             }
             if (blk_beg >= blk_end) {                 // this half has no column block (NT <= 32): still release the buffer
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                mbar_arrive(tempty_bar(ab));
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(ab));
             }
         }
     } else if (warp == PROD_WARPS + EPI_WARPS) {
@@ -306,8 +409,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_BYTES;
                     const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + b_bytes;
+                    const int ksteps = min(BK / 8, (p.K - c * BK + 7) / 8);     // the last chunk may be mostly padding
 #pragma unroll
                     for (int kk = 0; kk < BK / 8; ++kk) {
+                        if (kk >= ksteps) break;
                         const uint64_t dah = umma_desc(a_hi + kk * 32), dal = umma_desc(a_lo + kk * 32);
                         const uint64_t dbh = umma_desc(b_hi + kk * 32), dbl = umma_desc(b_lo + kk * 32);
                         // The fp32 accumulate of the tensor core truncates (error ~1 ulp of the accumulator per MMA, biased), so
@@ -316,9 +421,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
                         const int nmain = p.nacc - 1;
                         const uint32_t d_main = tmem_d + (uint32_t)((c % nmain) * p.tmem_cols);
                         const uint32_t d_aux = tmem_d + (uint32_t)(nmain * p.tmem_cols);
+#ifndef MRB_DIAG_NOMMA
                         umma_tf32(d_aux, dal, dbh, idesc, (c | kk) != 0);
                         umma_tf32(d_aux, dah, dbl, idesc, 1);
                         umma_tf32(d_main, dah, dbh, idesc, (c >= nmain) || kk != 0);
+#endif
                     }
                     umma_commit(empty_bar(s));                 // stage reusable once these MMAs retire
                 }
@@ -391,11 +498,22 @@ __global__ void k_pack_b(PackParams p) {
 
 struct Plan {
     int NT, ntiles, nchunks, tmem_cols, nacc;
+    int stages, stage_bytes;
     size_t image_bytes;
 };
 
+static int tune_nt_max() {   // TEMPORARY tuning hook
+    static int v = 0;
+    if (!v) { const char* e = getenv("MRB_TC_NT"); v = e ? atoi(e) : 256; }
+    return v;
+}
+
+// Column tile: <= 128 columns per CTA tile, so that two (main + cross-term) accumulator sets fit the 512 TMEM columns and
+// the epilogue of tile j overlaps the MMAs of tile j+1, and a stage is <= 64 KB (3-deep ring).  Consecutive tiles of a
+// CTA share their A rows (second read from L2).
 static Plan make_plan(int K, int N) {
     Plan pl;
+    const int NT_MAX = tune_nt_max();
     pl.ntiles = (N + NT_MAX - 1) / NT_MAX;
     const int per = (N + pl.ntiles - 1) / pl.ntiles;
     pl.NT = ((per + 15) / 16) * 16;
@@ -412,6 +530,8 @@ static Plan make_plan(int K, int N) {
         while (pl.nacc * 2 <= want) pl.nacc *= 2;      // TMEM allocations are powers of two
     }
     pl.image_bytes = (size_t)pl.ntiles * pl.nchunks * 2 * pl.NT * BK * 4;
+    pl.stage_bytes = 2 * A_BYTES + 2 * pl.NT * BK * 4;
+    pl.stages = min(TC_MAX_STAGES, TC_RING_BYTES / pl.stage_bytes);
     return pl;
 }
 
@@ -433,9 +553,15 @@ struct ParamsTN {
     int chunks_per_split;
     float* C0; float* C1;         // columns [0, n_split) -> C0 (ld ldc), [n_split, N) -> C1
     int n_split, ldc;
+    int tail;                     // 0..TN_TAIL_MAX extra rows [Kin, Kin + tail) of C, accumulated on the CUDA cores by tile 0
 };
+constexpr int TN_TAIL_MAX = 4;
 
-__global__ void __launch_bounds__(THREADS, 1) k_gemm_tn(ParamsTN p) {
+constexpr int TN_PROD_WARPS = 8;                       // warp w stages vertices [4w, 4w+4) of every chunk = 16-byte k chunk w
+constexpr int TN_THREADS = (TN_PROD_WARPS + 1) * 32;   // producers (also the epilogue) | MMA issuer
+constexpr int TN_PREFETCH = 1;                         // chunks in flight per producer thread (registers)
+
+__global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tn(ParamsTN p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -458,11 +584,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn(ParamsTN p) {
     while (tmem_cols < NT) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 128); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), TN_PROD_WARPS); mbar_init(empty_bar(s), 1); }
         mbar_init(tfull_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == TN_PROD_WARPS) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"(tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -472,78 +598,101 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn(ParamsTN p) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot;
 
-    if (warp < 4) {
+    if (warp < TN_PROD_WARPS) {
         if (nchunks > 0) {
-            // ===== producers: warp w stages vertices [8w, 8w+8) of every chunk (= k-block w) ==========================
-            // warp w stages vertices [8w, 8w+8) of every chunk = 16-byte k-chunks 2w and 2w+1 of each tile row
-            float xa[32];            // [mb 0..3][kc 0..1][t 0..3]
-            float gb[64];            // [nb 0..7][kc 0..1][t 0..3]
-            auto load_chunk = [&](int c) {
-                const int v0 = c * BK + warp * 8;
+            // ===== producers ==========================================================================================
+            // lane = row (feature i / column j) of a 32-row block; the 4 vertices of the warp form the 16-byte k chunk `warp`
+            // of that row.  Loads use clamped, always-valid addresses and are zero-masked at store time, so no instruction
+            // of the load phase depends on a loaded value and TN_PREFETCH chunks stay in flight.
+            float xa[TN_PREFETCH][16];           // [mb 0..3][t 0..3]
+            float gb[TN_PREFETCH][32];           // [nb 0..7][t 0..3]
+            // Tail rows (the stage inputs are 128 k + 3 wide: a further 128-row UMMA tile would be 98 % padding and would
+            // stage G once more): the producers of tile 0 already hold G[v, j] in registers, so they also load the `tail`
+            // extra X columns of their vertices (warp-uniform loads) and keep C[Kin + m, j] partial sums on the CUDA cores.
+            const int ntail = (blockIdx.x == 0) ? p.tail : 0;
+            float xt[TN_PREFETCH][4 * TN_TAIL_MAX];   // [t 0..3][m]
+            float tacc[TN_TAIL_MAX][8];               // [m][nb]: column j = nb * 32 + lane
 #pragma unroll
-                for (int kc = 0; kc < 2; ++kc)
+            for (int m = 0; m < TN_TAIL_MAX; ++m)
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const int v = v0 + kc * 4 + t;
-                        const bool vin = v < p.V;
+                for (int nb = 0; nb < 8; ++nb) tacc[m][nb] = 0.f;
+            auto load_chunk = [&](int c, float (&x)[16], float (&g)[32], float (&xtail)[4 * TN_TAIL_MAX]) {
+                const int v0 = c * BK + warp * 4;
 #pragma unroll
-                        for (int mb = 0; mb < 4; ++mb) {
-                            const int i = i0 + mb * 32 + lane;
-                            xa[(mb * 2 + kc) * 4 + t] = (vin && i < p.Kin) ? __ldg(p.X + (size_t)v * p.ldx + i) : 0.f;
-                        }
+                for (int t = 0; t < 4; ++t) {
+                    const int v = min(v0 + t, p.V - 1);
 #pragma unroll
-                        for (int nb = 0; nb < 8; ++nb) {
-                            const int j = nb * 32 + lane;
-                            gb[(nb * 2 + kc) * 4 + t] = (vin && j < NT) ? __ldg(p.G + (size_t)v * p.ldg + j) : 0.f;
-                        }
-                    }
+                    for (int m = 0; m < TN_TAIL_MAX; ++m)
+                        if (m < ntail) xtail[t * TN_TAIL_MAX + m] = __ldg(p.X + (size_t)v * p.ldx + p.Kin + m);
+#pragma unroll
+                    for (int mb = 0; mb < 4; ++mb)
+                        x[mb * 4 + t] = __ldg(p.X + (size_t)v * p.ldx + min(i0 + mb * 32 + lane, p.Kin - 1));
+#pragma unroll
+                    for (int nb = 0; nb < 8; ++nb)
+                        if (nb * 32 < NT) g[nb * 4 + t] = __ldg(p.G + (size_t)v * p.ldg + min(nb * 32 + lane, NT - 1));
+                }
             };
-            auto split_store = [&](unsigned char* hi_t, unsigned char* lo_t, int row, int kchunk, const float* v) {
-                const int off = (row >> 3) * 1024 + (row & 7) * 128 + (((kchunk ^ (row & 7)) & 7) << 4);
+            // nvalid: how many of the 4 vertices of this 16-byte k chunk exist (the rest is zero padding)
+            auto split_store = [&](unsigned char* hi_t, unsigned char* lo_t, int row, const float* v, int nvalid) {
+                const int off = (row >> 3) * 1024 + (row & 7) * 128 + (((warp ^ (row & 7)) & 7) << 4);
+                const float v0 = nvalid > 0 ? v[0] : 0.f, v1 = nvalid > 1 ? v[1] : 0.f, v2 = nvalid > 2 ? v[2] : 0.f,
+                            v3 = nvalid > 3 ? v[3] : 0.f;
                 float4 h, l;
-                h.x = tf32_rna(v[0]); h.y = tf32_rna(v[1]); h.z = tf32_rna(v[2]); h.w = tf32_rna(v[3]);
-                l.x = tf32_rna(v[0] - h.x); l.y = tf32_rna(v[1] - h.y); l.z = tf32_rna(v[2] - h.z); l.w = tf32_rna(v[3] - h.w);
+                h.x = tf32_rna(v0); h.y = tf32_rna(v1); h.z = tf32_rna(v2); h.w = tf32_rna(v3);
+                l.x = tf32_rna(v0 - h.x); l.y = tf32_rna(v1 - h.y); l.z = tf32_rna(v2 - h.z); l.w = tf32_rna(v3 - h.w);
                 *reinterpret_cast<float4*>(hi_t + off) = h;
                 *reinterpret_cast<float4*>(lo_t + off) = l;
             };
-            load_chunk(c_beg);
-            for (int c = 0; c < nchunks; ++c) {
-                const int s = c & 1, use = c >> 1;
-                if (use > 0) mbar_wait(empty_bar(s), (use - 1) & 1);
-                unsigned char* a_hi = smem + s * STAGE_BYTES;
-                unsigned char* a_lo = a_hi + A_BYTES;
-                unsigned char* b_hi = a_hi + 2 * A_BYTES;
-                unsigned char* b_lo = b_hi + b_bytes;
 #pragma unroll
-                for (int kc = 0; kc < 2; ++kc) {
+            for (int d = 0; d < TN_PREFETCH; ++d)
+                if (d < nchunks) load_chunk(c_beg + d, xa[d], gb[d], xt[d]);
+            for (int cb = 0; cb < nchunks; cb += TN_PREFETCH) {
 #pragma unroll
-                    for (int mb = 0; mb < 4; ++mb)
-                        split_store(a_hi, a_lo, mb * 32 + lane, warp * 2 + kc, &xa[(mb * 2 + kc) * 4]);
+                for (int d = 0; d < TN_PREFETCH; ++d) {
+                    const int c = cb + d;
+                    if (c < nchunks) {
+                        const int s = c % STAGES, use = c / STAGES;
+                        if (use > 0) mbar_wait(empty_bar(s), (use - 1) & 1);
+                        unsigned char* a_hi = smem + s * STAGE_BYTES;
+                        unsigned char* a_lo = a_hi + A_BYTES;
+                        unsigned char* b_hi = a_hi + 2 * A_BYTES;
+                        unsigned char* b_lo = b_hi + b_bytes;
+                        const int vleft = p.V - ((c_beg + c) * BK + warp * 4);          // vertices left from this k chunk on
 #pragma unroll
-                    for (int nb = 0; nb < 8; ++nb)
-                        if (nb * 32 < NT) split_store(b_hi, b_lo, nb * 32 + lane, warp * 2 + kc, &gb[(nb * 2 + kc) * 4]);
+                        for (int mb = 0; mb < 4; ++mb)
+                            split_store(a_hi, a_lo, mb * 32 + lane, &xa[d][mb * 4], (i0 + mb * 32 + lane < p.Kin) ? vleft : 0);
+#pragma unroll
+                        for (int nb = 0; nb < 8; ++nb)
+                            if (nb * 32 < NT) split_store(b_hi, b_lo, nb * 32 + lane, &gb[d][nb * 4], vleft);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(full_bar(s));
+                        if (ntail) {
+#pragma unroll
+                            for (int t = 0; t < 4; ++t)
+#pragma unroll
+                                for (int m = 0; m < TN_TAIL_MAX; ++m) {
+                                    const float xv = (m < ntail && t < vleft) ? xt[d][t * TN_TAIL_MAX + m] : 0.f;
+#pragma unroll
+                                    for (int nb = 0; nb < 8; ++nb)
+                                        if (nb * 32 < NT) tacc[m][nb] = fmaf(xv, gb[d][nb * 4 + t], tacc[m][nb]);
+                                }
+                        }
+                        if (c + TN_PREFETCH < nchunks) load_chunk(c_beg + c + TN_PREFETCH, xa[d], gb[d], xt[d]);
+                    }
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_arrive(full_bar(s));
-                if (c + 1 < nchunks) load_chunk(c_beg + c + 1);
             }
             // ===== epilogue: TMEM -> registers -> vectorised fp32 reductions into C ========================================
+            // warp w reads TMEM lane quadrant w % 4 (rows) and the column half w / 4
             mbar_wait(tfull_bar, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int i = i0 + warp * 32 + lane;       // TMEM lane = row of the tile
-            for (int c0 = 0; c0 < NT; c0 += 32) {
+            const int ew = warp & 3, half = warp >> 2;
+            const int i = i0 + ew * 32 + lane;          // TMEM lane = row of the tile
+            const int nblk = NT / 32, blk_beg = half * ((nblk + 1) / 2), blk_end = half ? nblk : (nblk + 1) / 2;
+            for (int blk = blk_beg; blk < blk_end; ++blk) {
+                const int c0 = blk * 32;
                 uint32_t v[32];
-                const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
-                      "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
-                      "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr));
+                tmem_ld32(tmem_d + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (i < p.Kin) {
                     float* dst = (c0 < p.n_split) ? p.C0 + (size_t)i * p.ldc + c0 : p.C1 + (size_t)i * p.ldc + (c0 - p.n_split);
@@ -555,12 +704,32 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn(ParamsTN p) {
                                      : "memory");
                 }
             }
+            if (ntail) {
+                // all MMAs have retired (tfull), so the stage ring is free: sum the 8 warps' partial tail rows there
+                float* red = reinterpret_cast<float*>(smem);                   // [warp][m][256]
+                asm volatile("bar.sync 1, %0;" ::"r"(TN_PROD_WARPS * 32));     // every producer warp is past its last stage use
+#pragma unroll
+                for (int m = 0; m < TN_TAIL_MAX; ++m)
+#pragma unroll
+                    for (int nb = 0; nb < 8; ++nb)
+                        if (m < ntail && nb * 32 < NT) red[(warp * TN_TAIL_MAX + m) * 256 + nb * 32 + lane] = tacc[m][nb];
+                asm volatile("bar.sync 1, %0;" ::"r"(TN_PROD_WARPS * 32));
+                for (int e = threadIdx.x; e < ntail * NT; e += TN_PROD_WARPS * 32) {
+                    const int m = e / NT, j = e - m * NT;
+                    float sum = 0.f;
+#pragma unroll
+                    for (int w = 0; w < TN_PROD_WARPS; ++w) sum += red[(w * TN_TAIL_MAX + m) * 256 + j];
+                    float* dst = (j < p.n_split) ? p.C0 + (size_t)(p.Kin + m) * p.ldc + j
+                                                 : p.C1 + (size_t)(p.Kin + m) * p.ldc + (j - p.n_split);
+                    atomicAdd(dst, sum);
+                }
+            }
         }
-    } else if (warp == 4) {
+    } else {
         if (lane == 0 && nchunks > 0) {
             const uint32_t idesc = umma_idesc(NT);
             for (int c = 0; c < nchunks; ++c) {
-                const int s = c & 1, use = c >> 1;
+                const int s = c % STAGES, use = c / STAGES;
                 mbar_wait(full_bar(s), use & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_BYTES;
@@ -581,7 +750,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_gemm_tn(ParamsTN p) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 4) {
+    if (warp == TN_PROD_WARPS) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(tmem_cols) : "memory");
     }
 }
@@ -621,9 +790,9 @@ extern "C" int mrb_gemm_tc(const float* A, int lda, int M, int K, const void* im
     if (M == 0) return MRB_OK;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
         if (e != cudaSuccess) {
-            set_error("gemm_tc: cannot reserve %d bytes of shared memory: %s", TC_SMEM_BYTES, cudaGetErrorString(e));
+            set_error("gemm_tc: cannot reserve %d bytes of shared memory: %s", TC_SMEM_LIMIT, cudaGetErrorString(e));
             return MRB_ERR_CUDA;
         }
         attr_set = true;
@@ -649,8 +818,9 @@ extern "C" int mrb_gemm_tc(const float* A, int lda, int M, int K, const void* im
         p.ntiles = pl.ntiles;
         p.accumulate = c0 > 0;
         p.C = C; p.ldc = ldc;
+        p.stages = pl.stages; p.stage_bytes = pl.stage_bytes;
         const int grid = min(p.mtiles * p.ntiles, kNumSMs);
-        k_gemm_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream_>>>(p);
+        k_gemm_tc<<<grid, TC_THREADS, pl.stages * pl.stage_bytes + EPI_BYTES + 1024 + 256, (cudaStream_t)stream_>>>(p);
     }
     return check_launch("gemm_tc");
 }
@@ -673,14 +843,16 @@ extern "C" int mrb_gemm_tc_wgrad(const float* X, int ldx, const float* G, int ld
         }
         attr_set = true;
     }
+    const int tail = (Kin > BM && Kin % BM <= TN_TAIL_MAX) ? Kin % BM : 0;   // e.g. the 3 position columns of a stage input
+    Kin -= tail;
     ParamsTN p;
     p.X = X; p.ldx = ldx; p.G = G; p.ldg = ldg; p.V = V; p.Kin = Kin; p.N = N; p.C0 = C0; p.C1 = C1; p.n_split = n_split;
-    p.ldc = ldc;
+    p.ldc = ldc; p.tail = tail;
     const int mtiles = ceil_div(Kin, BM);
     const int total_chunks = ceil_div(V, BK);
     int splits = max(1, min(total_chunks, kNumSMs / mtiles));
     p.chunks_per_split = min(ceil_div(total_chunks, splits), 32);    // <= 384 MMAs chained per accumulator (truncating adds)
     splits = ceil_div(total_chunks, p.chunks_per_split);
-    k_gemm_tn<<<dim3(mtiles, splits), THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(p);
+    k_gemm_tn<<<dim3(mtiles, splits), TN_THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(p);
     return check_launch("gemm_tc_wgrad");
 }
