@@ -11,7 +11,7 @@ import torch.nn as nn
 from torch import Tensor
 
 from .layers import Cubify, ResVertixRefineShapenet, VertixRefinePix3D, VertixRefineShapeNet
-from .loss_functions import batched_mesh_loss
+from .loss_functions import batched_mesh_loss, mesh_loss
 
 
 class MeshTargets:
@@ -55,6 +55,8 @@ class RefinementHead(nn.Module):
             stages.append(cls(alignment_size=alignment_channels, use_input_features=True,
                               num_features=vertex_feature_dim))
         self.refineStages = nn.ModuleList(stages)
+        self.overlap_losses = True          # training: per-stage losses on a second CUDA stream (see forward)
+        self._loss_stream = None
 
     def forward(self, voxel_probs: Tensor, feature_maps: Union[Tensor, List[Tensor]], image_sizes,
                 targets: Optional[MeshTargets] = None, mesh_index: Optional[List[int]] = None,
@@ -63,17 +65,45 @@ class RefinementHead(nn.Module):
             raise ValueError("In training mode, targets should be passed")
         mesh_index = [1 for _ in image_sizes] if mesh_index is None else mesh_index
         pos0, vertice_index, faces, face_index, adj_index = self.cubify(voxel_probs)
-        pos1, feats = self.refineStages[0](vertice_index, feature_maps, adj_index, pos0, image_sizes,
-                                           mesh_index=mesh_index)
-        positions = [pos0, pos1]
-        for stage in self.refineStages[1:]:
+        positions = [pos0]
+        feats = None
+        overlap = self.training and self.overlap_losses and voxel_probs.is_cuda
+        if overlap:
+            main = torch.cuda.current_stream()
+            if self._loss_stream is None or self._loss_stream.device != voxel_probs.device:
+                self._loss_stream = torch.cuda.Stream(device=voxel_probs.device)
+            side = self._loss_stream
+        terms = []
+        for s, stage in enumerate(self.refineStages):
+            kw = {} if feats is None else {"vertex_features": feats}
             new_pos, feats = stage(vertice_index, feature_maps, adj_index, positions[-1], image_sizes,
-                                   mesh_index=mesh_index, vertex_features=feats)
+                                   mesh_index=mesh_index, **kw)
             positions.append(new_pos)
+            if overlap:
+                # The loss of stage s depends only on its positions.  It is issued on a second stream right away, so that its
+                # long, issue-bound nearest-neighbour kernels share the SMs with the tensor-core / gather kernels of stage
+                # s + 1 (those leave ~75 % of the issue slots idle) and the GPU never waits for launches -- same terms, same
+                # order of sampler draws as batched_mesh_loss(positions[1:], ...) after the loop (reference
+                # shapenet_model.py:92-95).  Autograd runs each backward node on the stream of its forward, so the backward
+                # passes overlap the same way.  (Stream priorities -- stages high, losses low -- were measured: no gain.)
+                side.wait_stream(main)
+                new_pos.record_stream(side)
+                with torch.cuda.stream(side):
+                    terms.append(mesh_loss(new_pos, faces, adj_index, vertice_index, face_index, targets,
+                                           randomness=None if loss_randomness is None else loss_randomness[s]))
         out = {}
         if self.training:
-            chamfer, normal, edge = batched_mesh_loss(positions[1:], faces, adj_index, vertice_index, face_index, targets,
-                                                      randomness=loss_randomness)
+            if overlap:
+                main.wait_stream(side)
+                for t in terms:
+                    for x in t:
+                        x.record_stream(main)
+                chamfer, normal, edge = terms[0]
+                for c, n, e in terms[1:]:
+                    chamfer, normal, edge = chamfer + c, normal + n, edge + e
+            else:
+                chamfer, normal, edge = batched_mesh_loss(positions[1:], faces, adj_index, vertice_index, face_index,
+                                                          targets, randomness=loss_randomness)
             out.update({"chamfer_loss": chamfer, "edge_loss": edge, "normal_loss": normal})
         else:
             out.update({"vertex_positions": positions, "edge_index": adj_index, "face_index": face_index,
