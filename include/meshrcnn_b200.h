@@ -76,6 +76,11 @@ int mrb_segment_ids(const int32_t* offsets, int nseg, int n, int32_t* ids, void*
  * gz = gout * (act > 0) formed on the fly (gout may be a strided view: ld_g >= D). */
 int mrb_graphconv_bwd_gather(const int32_t* rowptr_t, const int32_t* col_t, int n, const float* gout, int ld_g,
                              const float* act, int ld_a, int D, float* gy, void* stream);
+/* Column concatenation of up to three row-major matrices (torch.cat(dim=1) of the stage inputs, reference
+ * meshRCNN/layers.py:160-165,241-252,321-334) into rows of pitch ld_out >= w0 + w1 + w2 floats; the pad columns are
+ * zero-filled.  A pitch that is a multiple of 4 keeps every row 16-byte aligned for the tcgen05 projection's producers. */
+int mrb_concat_cols(const float* s0, int w0, int ld0, const float* s1, int w1, int ld1, const float* s2, int w2, int ld2,
+                    int n, float* out, int ld_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Dense contraction  C = op(A) * op(B) + beta * C  (row-major fp32, exact fp32 accumulate on the CUDA cores).

@@ -193,6 +193,28 @@ __global__ void k_segment_ids(const int32_t* __restrict__ offsets, int nseg, int
     ids[i] = lo;
 }
 
+// out[r, :] = [s0[r, :w0] | s1[r, :w1] | s2[r, :w2] | 0 ...] with a row pitch of ld_out >= w0 + w1 + w2 floats
+// (torch.cat of the stage inputs, reference layers.py:160-165,241-252,321-334, written with 16-byte aligned rows)
+__global__ void __launch_bounds__(256) k_concat_cols(const float* __restrict__ s0, int w0, int ld0, const float* __restrict__ s1,
+                                                     int w1, int ld1, const float* __restrict__ s2, int w2, int ld2, int n,
+                                                     float* __restrict__ out, int ld_out) {
+    // one warp per row at a time: lanes stride over the columns (coalesced reads and writes, no index division)
+    const int warps = gridDim.x * (blockDim.x >> 5);
+    for (int r = blockIdx.x * (blockDim.x >> 5) + warp_id(); r < n; r += warps) {
+        const float* r0 = s0 + (size_t)r * ld0;
+        const float* r1 = s1 + (size_t)r * ld1 - w0;
+        const float* r2 = s2 + (size_t)r * ld2 - w0 - w1;
+        float* o = out + (size_t)r * ld_out;
+        for (int c = lane_id(); c < ld_out; c += 32) {
+            float v = 0.f;
+            if (c < w0) v = r0[c];
+            else if (c < w0 + w1) v = r1[c];
+            else if (c < w0 + w1 + w2) v = r2[c];
+            o[c] = v;
+        }
+    }
+}
+
 }  // namespace graph
 }  // namespace mrb
 
@@ -265,4 +287,14 @@ extern "C" int mrb_graphconv_bwd_gather(const int32_t* rowptr_t, const int32_t* 
     if (vec) k_gather_bwd<true><<<ceil_div(n, 8), 256, 0, s>>>(rowptr_t, col_t, n, gout, ld_g, act, ld_a, D, gy);
     else k_gather_bwd<false><<<ceil_div(n, 8), 256, 0, s>>>(rowptr_t, col_t, n, gout, ld_g, act, ld_a, D, gy);
     return check_launch("graphconv_bwd_gather");
+}
+
+extern "C" int mrb_concat_cols(const float* s0, int w0, int ld0, const float* s1, int w1, int ld1, const float* s2, int w2,
+                               int ld2, int n, float* out, int ld_out, void* stream_) {
+    MRB_REQUIRE(out && s0 && w0 > 0 && (w1 == 0 || s1) && (w2 == 0 || s2), "concat_cols: null pointer");
+    MRB_REQUIRE(w1 >= 0 && w2 >= 0 && ld0 >= w0 && ld1 >= w1 && ld2 >= w2 && ld_out >= w0 + w1 + w2, "concat_cols: bad widths");
+    if (n <= 0) return MRB_OK;
+    const int blocks = (int)min((long long)16 * kNumSMs, ceil_div64(n, 8));
+    k_concat_cols<<<blocks, 256, 0, (cudaStream_t)stream_>>>(s0, w0, ld0, s1, w1, ld1, s2, w2, ld2, n, out, ld_out);
+    return check_launch("concat_cols");
 }

@@ -116,6 +116,56 @@ def _f32c(t: Tensor) -> Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _rows(t: Tensor) -> Tensor:
+    """fp32 matrix whose rows are dense (stride(1) == 1) but may have a row pitch > width (a column slice of a wider
+    buffer, e.g. the 16-byte aligned rows ``concat_cols`` produces): the kernels take the pitch as ld, no copy is made."""
+    if t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1]:
+        return t
+    return _f32c(t)
+
+
+def _pitch(width: int) -> int:
+    return (width + 3) // 4 * 4
+
+
+def _padded_rows(n: int, width: int, device) -> Tensor:
+    """n x width view of a buffer whose rows start on 16-byte boundaries."""
+    return torch.empty(n, _pitch(width), dtype=torch.float32, device=device)[:, :width]
+
+
+class _ConcatCols(torch.autograd.Function):
+    """torch.cat(parts, dim=1) into rows padded to a multiple of 4 floats (one kernel); the backward hands out column
+    slices of the upstream gradient (views, no copies)."""
+
+    @staticmethod
+    def forward(ctx, *parts):
+        ps = [_rows(p) for p in parts]
+        _require_cuda(ps[0], "concat_cols")
+        n = ps[0].shape[0]
+        widths = [p.shape[1] for p in ps]
+        out = torch.empty(n, _pitch(sum(widths)), dtype=torch.float32, device=ps[0].device)
+        a = [(p.data_ptr(), p.shape[1], p.stride(0)) for p in ps] + [(None, 0, 0)] * (3 - len(ps))
+        _lib.call("mrb_concat_cols", a[0][0], a[0][1], a[0][2], a[1][0], a[1][1], a[1][2], a[2][0], a[2][1], a[2][2], n,
+                  _lib.ptr(out), out.shape[1])
+        ctx.widths = widths
+        return out[:, :sum(widths)]
+
+    @staticmethod
+    def backward(ctx, g):
+        outs, off = [], 0
+        for i, w in enumerate(ctx.widths):
+            outs.append(g[:, off:off + w] if ctx.needs_input_grad[i] else None)
+            off += w
+        return tuple(outs)
+
+
+def concat_cols(parts: Sequence[Tensor]) -> Tensor:
+    """``torch.cat(parts, dim=1)`` for 1-3 fp32 CUDA matrices with 16-byte aligned output rows (a strided view)."""
+    if not 1 <= len(parts) <= 3:
+        raise RuntimeError("concat_cols: 1 to 3 parts")
+    return _ConcatCols.apply(*parts)
+
+
 # ----------------------------------------------------------------------------------------------------------
 # dense contraction on the library's GEMM
 # ----------------------------------------------------------------------------------------------------------
@@ -139,15 +189,16 @@ class _MatMul(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, trans_w):
         _require_cuda(x, "matmul")
-        x, w = _f32c(x), _f32c(w)
+        x, w = _rows(x), _f32c(w)
         M, K = x.shape
+        ldx = x.stride(0)
         N = w.shape[0] if trans_w else w.shape[1]
         y = torch.empty(M, N, dtype=torch.float32, device=x.device)
         if _use_tc(K, N):
             img = tc_pack(w, None, 1 if trans_w else N, K if trans_w else 1, 0, 0, K, N)
-            tc_gemm(_lib.ptr(x), K, M, K, img, N, _lib.ptr(y), N)
+            tc_gemm(x.data_ptr(), ldx, M, K, img, N, _lib.ptr(y), N)
         else:
-            _gemm(False, trans_w, M, N, K, _lib.ptr(x), K, _lib.ptr(w), w.shape[1], 0.0, _lib.ptr(y), N)
+            _gemm(False, trans_w, M, N, K, x.data_ptr(), ldx, _lib.ptr(w), w.shape[1], 0.0, _lib.ptr(y), N)
         ctx.save_for_backward(x, w)
         ctx.trans_w = trans_w
         return y
@@ -157,27 +208,29 @@ class _MatMul(torch.autograd.Function):
         x, w = ctx.saved_tensors
         gy = _f32c(gy)
         M, K = x.shape
+        ldx = x.stride(0)
         N = gy.shape[1]
         gx = gw = None
         if ctx.needs_input_grad[0]:
-            gx = torch.empty_like(x)
+            gx = _padded_rows(M, K, x.device)
+            ldg = gx.stride(0)
             # gx = gy @ w (trans_w) or gy @ w^T :  logical B(k = out index, n = in index)
             if _use_tc(N, K):
                 img = tc_pack(w, None, K if ctx.trans_w else 1, 1 if ctx.trans_w else N, 0, 0, N, K)
-                tc_gemm(_lib.ptr(gy), N, M, N, img, K, _lib.ptr(gx), K)
+                tc_gemm(_lib.ptr(gy), N, M, N, img, K, gx.data_ptr(), ldg)
             else:
-                _gemm(False, not ctx.trans_w, M, K, N, _lib.ptr(gy), N, _lib.ptr(w), w.shape[1], 0.0, _lib.ptr(gx), K)
+                _gemm(False, not ctx.trans_w, M, K, N, _lib.ptr(gy), N, _lib.ptr(w), w.shape[1], 0.0, gx.data_ptr(), ldg)
         if ctx.needs_input_grad[1]:
             if _use_tc_wgrad(M, N):       # x^T @ gy (K x N) on the tensor cores; nn.Linear stores the transpose
                 gwt = torch.zeros(K, N, dtype=torch.float32, device=x.device)
-                _lib.call("mrb_gemm_tc_wgrad", _lib.ptr(x), K, _lib.ptr(gy), N, M, K, N, _lib.ptr(gwt), None, N, N)
+                _lib.call("mrb_gemm_tc_wgrad", x.data_ptr(), ldx, _lib.ptr(gy), N, M, K, N, _lib.ptr(gwt), None, N, N)
                 gw = gwt.t().contiguous() if ctx.trans_w else gwt
             else:
                 gw = torch.empty_like(w)
                 if ctx.trans_w:   # w: N x K ; gw = gy^T @ x
-                    _gemm(True, False, N, K, M, _lib.ptr(gy), N, _lib.ptr(x), K, 0.0, _lib.ptr(gw), K)
+                    _gemm(True, False, N, K, M, _lib.ptr(gy), N, x.data_ptr(), ldx, 0.0, _lib.ptr(gw), K)
                 else:             # w: K x N ; gw = x^T @ gy
-                    _gemm(True, False, K, N, M, _lib.ptr(x), K, _lib.ptr(gy), N, 0.0, _lib.ptr(gw), N)
+                    _gemm(True, False, K, N, M, x.data_ptr(), ldx, _lib.ptr(gy), N, 0.0, _lib.ptr(gw), N)
         return gx, gw, None
 
 
@@ -232,17 +285,18 @@ class _GraphConv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w0, w1, topo):
         _require_cuda(x, "GraphConv")
-        x, w0, w1 = _f32c(x), _f32c(w0), _f32c(w1)
+        x, w0, w1 = _rows(x), _f32c(w0), _f32c(w1)
         n, K = x.shape
+        ldx, xp = x.stride(0), x.data_ptr()
         D = w0.shape[1]
         y = torch.empty(n, 2 * D, dtype=torch.float32, device=x.device)
         yp = _lib.ptr(y)
         if _use_tc(K, 2 * D):      # one tensor-core pass over x for [x W0 | x W1]
             img = tc_pack(w0, w1, D, 1, 1, D, K, 2 * D)
-            tc_gemm(_lib.ptr(x), K, n, K, img, 2 * D, yp, 2 * D)
+            tc_gemm(xp, ldx, n, K, img, 2 * D, yp, 2 * D)
         else:
-            _gemm(False, False, n, D, K, _lib.ptr(x), K, _lib.ptr(w0), D, 0.0, yp, 2 * D)
-            _gemm(False, False, n, D, K, _lib.ptr(x), K, _lib.ptr(w1), D, 0.0, yp + 4 * D, 2 * D)
+            _gemm(False, False, n, D, K, xp, ldx, _lib.ptr(w0), D, 0.0, yp, 2 * D)
+            _gemm(False, False, n, D, K, xp, ldx, _lib.ptr(w1), D, 0.0, yp + 4 * D, 2 * D)
         out = torch.empty(n, D, dtype=torch.float32, device=x.device)
         _gather(topo.rowptr, topo.col, n, yp, 2 * D, yp + 4 * D, 2 * D, D, True, _lib.ptr(out), D)
         ctx.save_for_backward(x, w0, w1, out)
@@ -254,6 +308,7 @@ class _GraphConv(torch.autograd.Function):
         x, w0, w1, out = ctx.saved_tensors
         topo = ctx.topo
         n, K = x.shape
+        ldx, xp = x.stride(0), x.data_ptr()
         D = w0.shape[1]
         # upstream gradients are often column slices of a wider matrix (autograd of torch.cat): read them in place
         if gout.dtype != torch.float32 or gout.stride(1) != 1 or gout.stride(0) < D:
@@ -269,25 +324,26 @@ class _GraphConv(torch.autograd.Function):
             _gather(topo.rowptr_t, topo.col_t, n, None, 0, gp, 2 * D, D, False, gp + 4 * D, 2 * D)
         gx = gw0 = gw1 = None
         if ctx.needs_input_grad[0]:
-            gx = torch.empty_like(x)
+            gx = _padded_rows(n, K, x.device)      # 16-byte aligned rows: coalesced epilogue of the tensor-core kernel
+            ldgx, gxp = gx.stride(0), gx.data_ptr()
             if _use_tc(2 * D, K):  # gx = [gz | A^T gz] @ [W0 | W1]^T in one pass
                 img = tc_pack(w0, w1, 1, D, 2, D, 2 * D, K)
-                tc_gemm(gp, 2 * D, n, 2 * D, img, K, _lib.ptr(gx), K)
+                tc_gemm(gp, 2 * D, n, 2 * D, img, K, gxp, ldgx)
             else:
-                _gemm(False, True, n, K, D, gp, 2 * D, _lib.ptr(w0), D, 0.0, _lib.ptr(gx), K)
-                _gemm(False, True, n, K, D, gp + 4 * D, 2 * D, _lib.ptr(w1), D, 1.0, _lib.ptr(gx), K)
+                _gemm(False, True, n, K, D, gp, 2 * D, _lib.ptr(w0), D, 0.0, gxp, ldgx)
+                _gemm(False, True, n, K, D, gp + 4 * D, 2 * D, _lib.ptr(w1), D, 1.0, gxp, ldgx)
         if (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) and _use_tc_wgrad(n, 2 * D) and D % 32 == 0:
             # dW0 | dW1 = x^T @ [gz | A^T gz]: one tensor-core pass over x and gy, reduced over the vertices
             gw = torch.zeros(2, K, D, dtype=torch.float32, device=x.device)
-            _lib.call("mrb_gemm_tc_wgrad", _lib.ptr(x), K, gp, 2 * D, n, K, 2 * D, _lib.ptr(gw), _lib.ptr(gw) + 4 * K * D, D, D)
+            _lib.call("mrb_gemm_tc_wgrad", xp, ldx, gp, 2 * D, n, K, 2 * D, _lib.ptr(gw), _lib.ptr(gw) + 4 * K * D, D, D)
             gw0, gw1 = gw[0], gw[1]
         else:
             if ctx.needs_input_grad[1]:
                 gw0 = torch.empty_like(w0)
-                _gemm(True, False, K, D, n, _lib.ptr(x), K, gp, 2 * D, 0.0, _lib.ptr(gw0), D)
+                _gemm(True, False, K, D, n, xp, ldx, gp, 2 * D, 0.0, _lib.ptr(gw0), D)
             if ctx.needs_input_grad[2]:
                 gw1 = torch.empty_like(w1)
-                _gemm(True, False, K, D, n, _lib.ptr(x), K, gp + 4 * D, 2 * D, 0.0, _lib.ptr(gw1), D)
+                _gemm(True, False, K, D, n, xp, ldx, gp + 4 * D, 2 * D, 0.0, _lib.ptr(gw1), D)
         return gx, gw0, gw1, None
 
 
@@ -327,15 +383,16 @@ class _VertAlign(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         pos_c, vert_mesh, mesh_info = ctx.saved_tensors
-        gout = _f32c(gout)
+        gout = _rows(gout)                       # usually a column slice of a stage-input gradient: read in place
         SV, ctot = gout.shape
+        ldg = gout.stride(0)
         grads = []
         off = 0
         for i, shape in enumerate(ctx.shapes):
             n_img, C, Hm, Wm = shape
             if ctx.needs_input_grad[3 + i]:
                 g = torch.zeros(shape, dtype=torch.float32, device=gout.device)
-                _lib.call("mrb_vert_align_bwd", _lib.ptr(gout) + 4 * off, ctot, n_img, C, Hm, Wm, _lib.ptr(pos_c),
+                _lib.call("mrb_vert_align_bwd", gout.data_ptr() + 4 * off, ldg, n_img, C, Hm, Wm, _lib.ptr(pos_c),
                           _lib.ptr(vert_mesh), _lib.ptr(mesh_info), SV, _lib.ptr(g))
                 grads.append(g.to(ctx.dtypes[i]))
             else:

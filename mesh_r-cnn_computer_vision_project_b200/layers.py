@@ -126,7 +126,7 @@ def _stage_input(vertex_positions, pooled, vertex_features, use_input_features):
         parts = [vertex_features] + parts
     else:
         assert not use_input_features
-    return torch.cat(parts, dim=1)
+    return F_.concat_cols(parts)
 
 
 class ResVertixRefineShapenet(nn.Module):
@@ -184,8 +184,8 @@ class VertixRefineShapeNet(nn.Module):
         projected = self.linear0(aligned)
         x = _stage_input(vertex_positions, projected, vertex_features, self.use_input_features)
         x = self.graphConv0(x, vertex_adjacency)
-        x = self.graphConv1(torch.cat([vertex_positions, x], dim=1), vertex_adjacency)
-        x = self.graphConv2(torch.cat([vertex_positions, x], dim=1), vertex_adjacency)
+        x = self.graphConv1(F_.concat_cols([vertex_positions, x]), vertex_adjacency)
+        x = self.graphConv2(F_.concat_cols([vertex_positions, x]), vertex_adjacency)
         delta = self.tanh(self.linear1(x))
         return vertex_positions + delta, x
 
@@ -212,7 +212,7 @@ class VertixRefinePix3D(nn.Module):
         aligned = self.vertAlign([back_bone_features], vertex_positions, vertice_index, image_sizes, mesh_index)
         x = _stage_input(vertex_positions, aligned, vertex_features, self.use_input_features)
         x = self.graphConv0(x, vertex_adjacency)
-        x = self.graphConv1(torch.cat([vertex_positions, x], dim=1), vertex_adjacency)
-        x = self.graphConv2(torch.cat([vertex_positions, x], dim=1), vertex_adjacency)
-        delta = self.tanh(self.linear(torch.cat([vertex_positions, x], dim=1)))
+        x = self.graphConv1(F_.concat_cols([vertex_positions, x]), vertex_adjacency)
+        x = self.graphConv2(F_.concat_cols([vertex_positions, x]), vertex_adjacency)
+        delta = self.tanh(self.linear(F_.concat_cols([vertex_positions, x])))
         return vertex_positions + delta, x

@@ -40,7 +40,12 @@ v, vi, f, fi, adj = cub(vox)
 SV, SF, E = v.shape[0], f.shape[0], adj.shape[1]
 byts = 4 * vox.numel() + 12 * SV + 24 * SF + 16 * E + 16 * 64
 t = timeit(lambda: cub(vox), n=5)
+with _lib.timed_calls() as tc:
+    for _ in range(5):
+        cub(vox)
 out["cubify_config4"] = {"SV": SV, "SF": SF, "E": E, "bytes": byts, "ms": t * 1e3, "GBps": byts / t / 1e9, "frac_hbm": byts / t / 1e9 / HBM,
+                         "ms_count_kernels": tc.ms["mrb_cubify_count"] / 5, "ms_emit_kernels": tc.ms["mrb_cubify_emit"] / 5,
+                         "GBps_emit_only": (12 * SV + 24 * SF + 16 * E) / (tc.ms["mrb_cubify_emit"] / 5) / 1e6,
                          "note": "whole Cubify.forward incl. the count read-back sync and output allocation"}
 del v, f, adj
 
@@ -61,10 +66,14 @@ def cloud(seed):
     c, _ = F_.sample_points(vv * 0.05, ff, vvi, ffi, P, seed=seed + 1)
     return c
 p, q = cloud(0), cloud(1000)
-for k in (0, 10):
-    t = timeit(lambda: F_.chamfer_knn(p, q, k), n=10, l2_flush=False)
-    out["chamfer_knn_config5_k%d" % k] = {"pairs_per_call": 2 * B * P * P, "ms": t * 1e3, "Gpairs_per_s": 2 * B * P * P / t / 1e9,
-                                          "note": "one call = both directions (+ top-k index sets when k>0), FP32-issue bound"}
+for algo in ("grid", "tiled"):
+    for k in (0, 10):
+        t = timeit(lambda: F_.knn_search(p, q, k, algo=algo), n=10, l2_flush=False)
+        out["chamfer_knn_config5_k%d_%s" % (k, algo)] = {
+            "pairs_per_call": 2 * B * P * P, "ms": t * 1e3, "Gpairs_per_s": 2 * B * P * P / t / 1e9,
+            "frac_of_bruteforce_issue_bound": 2 * B * P * P / t / 1e12 / (148 * 128 * 1.965e9 / 1e12 / 4),
+            "note": "one call = both directions (+ top-k index sets when k>0); 'grid' = exact cell-grid search (default), "
+                    "'tiled' = shared-memory tiled scan with x pruning; bound = brute-force scan at 4 instr/pair"}
 
 # ---- GraphConv pieces at config 3 per-GPU size (SV ~ 220k) -----------------------------------------------------------
 v, vi, f, fi, adj = Cubify(0.2)(synthetic.blob_voxels(32, 48, 0).to(dev))
@@ -78,23 +87,35 @@ t = timeit(gather)
 byts = 4 * SV * 128 * 3 + 4 * (E + SV + 1)          # self + neighbour matrix read once + output
 out["csr_gather_relu_config3"] = {"SV": SV, "E": E, "bytes_compulsory": byts, "ms": t * 1e3, "GBps": byts / t / 1e9,
                                   "frac_hbm": byts / t / 1e9 / HBM, "bytes_no_reuse": 4 * 128 * (E + 2 * SV)}
+TF32_PEAK = PEAKS.get("bf16_tflops", 2250.0) / 2          # dense TF32 = half the measured bf16 rate
+r4 = lambda v: (v + 3) // 4 * 4
 for (K, N) in ((131, 256), (259, 256), (387, 256), (256, 131), (256, 387)):
-    a = torch.randn(SV, K, device=dev); w = torch.randn(K, N, device=dev); c = torch.empty(SV, N, device=dev)
-    img = F_.tc_pack(w, None, N, 1, 0, 0, K, N)
-    t = timeit(lambda: F_.tc_gemm(_lib.ptr(a), K, SV, K, img, N, _lib.ptr(c), N))
-    byts = 4 * SV * (K + N)
-    out["gemm_tc_%dx%d_config3" % (K, N)] = {"M": SV, "bytes": byts, "ms": t * 1e3, "GBps": byts / t / 1e9, "frac_hbm": byts / t / 1e9 / HBM,
-                                             "TFLOPs_fp32_equiv": 2 * SV * K * N / t / 1e12, "TFLOPs_tf32_issued": 6 * SV * K * N / t / 1e12}
-    del a, c
-x = torch.randn(SV, 387, device=dev); gy = torch.randn(SV, 256, device=dev); gw = torch.zeros(2, 387, 128, device=dev)
-def wgrad():
-    gw.zero_()
-    _lib.call("mrb_gemm_tc_wgrad", _lib.ptr(x), 387, _lib.ptr(gy), 256, SV, 387, 256, _lib.ptr(gw), _lib.ptr(gw) + 4 * 387 * 128, 128, 128)
-t = timeit(wgrad)
-byts = 4 * SV * (387 + 256)
-out["gemm_tc_wgrad_387x256_config3"] = {"bytes": byts, "ms": t * 1e3, "GBps": byts / t / 1e9, "frac_hbm": byts / t / 1e9 / HBM,
-                                        "TFLOPs_fp32_equiv": 2 * SV * 387 * 256 / t / 1e12}
-del x, gy
+    for pad in (False, True):
+        lda, ldc = (r4(K), r4(N)) if pad else (K, N)
+        if pad and lda == K and ldc == N:
+            continue
+        a = torch.randn(SV, lda, device=dev); w = torch.randn(K, N, device=dev); c = torch.empty(SV, ldc, device=dev)
+        img = F_.tc_pack(w, None, N, 1, 0, 0, K, N)
+        t = timeit(lambda: F_.tc_gemm(_lib.ptr(a), lda, SV, K, img, N, _lib.ptr(c), ldc))
+        byts = 4 * SV * (K + N)
+        out["gemm_tc_%dx%d_config3%s" % (K, N, "_rows16B" if pad else "")] = {
+            "M": SV, "lda": lda, "ldc": ldc, "bytes": byts, "ms": t * 1e3, "GBps": byts / t / 1e9, "frac_hbm": byts / t / 1e9 / HBM,
+            "TFLOPs_fp32_equiv": 2 * SV * K * N / t / 1e12, "TFLOPs_tf32_issued": 6 * SV * K * N / t / 1e12,
+            "frac_tensor_tf32": 6 * SV * K * N / t / 1e12 / TF32_PEAK}
+        del a, c
+gy = torch.randn(SV, 256, device=dev)
+for Kin in (131, 259, 387):
+    x = torch.randn(SV, Kin, device=dev); gw = torch.zeros(2, Kin, 128, device=dev)
+    def wgrad():
+        gw.zero_()
+        _lib.call("mrb_gemm_tc_wgrad", _lib.ptr(x), Kin, _lib.ptr(gy), 256, SV, Kin, 256, _lib.ptr(gw), _lib.ptr(gw) + 4 * Kin * 128, 128, 128)
+    t = timeit(wgrad)
+    byts = 4 * SV * (Kin + 256)
+    out["gemm_tc_wgrad_%dx256_config3" % Kin] = {"bytes": byts, "ms": t * 1e3, "GBps": byts / t / 1e9, "frac_hbm": byts / t / 1e9 / HBM,
+                                                 "TFLOPs_fp32_equiv": 2 * SV * Kin * 256 / t / 1e12,
+                                                 "frac_tensor_tf32": 6 * SV * Kin * 256 / t / 1e12 / TF32_PEAK}
+    del x
+del gy
 
 # ---- VertexAlign at config 3 (ShapeNet maps, 3840 channels) and config 2 (Pix3D) ---------------------------------------------
 fm = [m.to(dev) for m in synthetic.feature_maps(32, synthetic.SHAPENET_MAPS, 0)]
