@@ -93,7 +93,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------
 # workload
 # ---------------------------------------------------------------------------------------------------------------
-KNN_DRAM_BYTES_PER_LAUNCH = 10.96e6      # ncu dram__bytes_read+write of one k_nn_grid<10> launch (profiles/)
+KNN_DRAM_BYTES_PER_LAUNCH = 11.74e6      # ncu dram__bytes_read+write of one k_nn_grid<10> launch (profiles/)
 
 
 def make_inputs(B, seed):
