@@ -69,3 +69,43 @@ def all_reduce_losses(losses: dict) -> dict:
     buf = torch.stack([losses[k].detach().float() for k in keys])
     dist.all_reduce(buf, op=dist.ReduceOp.SUM)
     return {k: buf[i] for i, k in enumerate(keys)}
+
+
+def _all_gather_ragged(t: Tensor, dim: int = 0) -> List[Tensor]:
+    """all_gather of tensors whose size along ``dim`` differs per rank (sizes exchanged first, payload padded to the max)."""
+    world = dist.get_world_size()
+    t = t.contiguous()
+    size = torch.tensor([t.shape[dim]], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(size) for _ in range(world)]
+    dist.all_gather(sizes, size)
+    sizes = [int(x) for x in sizes]
+    mx = max(sizes)
+    moved = t.movedim(dim, 0)
+    pad = torch.zeros((mx,) + tuple(moved.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[:moved.shape[0]] = moved
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad)
+    return [b[:n].movedim(0, dim) for b, n in zip(bufs, sizes)]
+
+
+def gather_eval_outputs(out: dict) -> dict:
+    """Eval-mode output dicts of all ranks merged into one packed batch on every rank -- the reference's
+    ``gather_GCN_outputs`` (dataParallel/gather.py:65-92): per-stage vertex positions and faces concatenated in rank
+    order, ``edge_index`` re-offset by the number of vertices of the preceding shards (:80-83), the per-mesh count lists
+    chained.  Keys: ``vertex_positions`` (list), ``edge_index``, ``faces``, ``vertice_index``, ``face_index``,
+    ``mesh_index``.  Without an initialised process group (or world size 1) the input is returned unchanged."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return out
+    world = dist.get_world_size()
+    lists = [None] * world
+    dist.all_gather_object(lists, {k: list(out[k]) for k in ("vertice_index", "face_index", "mesh_index")})
+    res = {k: [x for d in lists for x in d[k]] for k in ("vertice_index", "face_index", "mesh_index")}
+    res["vertex_positions"] = [torch.cat(_all_gather_ragged(p, 0), 0) for p in out["vertex_positions"]]
+    res["faces"] = torch.cat(_all_gather_ragged(out["faces"], 0), 0)
+    offsets, run = [], 0
+    for d in lists:
+        offsets.append(run)
+        run += sum(d["vertice_index"])
+    edges = _all_gather_ragged(out["edge_index"], 1)
+    res["edge_index"] = torch.cat([e + off for e, off in zip(edges, offsets)], 1)
+    return res

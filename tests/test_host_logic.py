@@ -113,6 +113,17 @@ ref.load_state_dict(lin.state_dict())
 ref(data).pow(2).sum().backward()                                       # SUM over shards == unsharded gradient
 for p, q in zip(lin.parameters(), ref.parameters()):
     assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-6), (rank, p.grad, q.grad)
+# eval outputs: ragged gather with the edge ids re-offset (reference gather.py:65-92)
+from meshrcnn_b200.sharding import gather_eval_outputs
+nv = [3, 2] if rank == 0 else [4]
+SV = sum(nv)
+mine = {"vertex_positions": [torch.full((SV, 3), float(rank)), torch.full((SV, 3), 10.0 + rank)],
+        "edge_index": torch.tensor([[0, SV - 1], [SV - 1, 0]]), "faces": torch.tensor([[0, 1, 2]] * (rank + 1)),
+        "vertice_index": nv, "face_index": [1] * len(nv), "mesh_index": [1] * len(nv)}
+g = gather_eval_outputs(mine)
+assert g["vertice_index"] == [3, 2, 4] and g["mesh_index"] == [1, 1, 1] and g["faces"].shape == (3, 3)
+assert g["vertex_positions"][0].shape == (9, 3) and float(g["vertex_positions"][1][5:].mean()) == 11.0
+assert g["edge_index"].tolist() == [[0, 4, 5, 8], [4, 0, 8, 5]], g["edge_index"].tolist()
 tot = all_reduce_losses({"chamfer_loss": torch.tensor(float(rank + 1)), "edge_loss": torch.tensor(2.0)})
 assert float(tot["chamfer_loss"]) == sum(range(1, world + 1)) and float(tot["edge_loss"]) == 2.0 * world
 dist.destroy_process_group()
