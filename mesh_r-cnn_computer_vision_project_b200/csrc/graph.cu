@@ -198,19 +198,32 @@ __global__ void k_segment_ids(const int32_t* __restrict__ offsets, int nseg, int
 __global__ void __launch_bounds__(256) k_concat_cols(const float* __restrict__ s0, int w0, int ld0, const float* __restrict__ s1,
                                                      int w1, int ld1, const float* __restrict__ s2, int w2, int ld2, int n,
                                                      float* __restrict__ out, int ld_out) {
-    // one warp per row at a time: lanes stride over the columns (coalesced reads and writes, no index division)
-    const int warps = gridDim.x * (blockDim.x >> 5);
-    for (int r = blockIdx.x * (blockDim.x >> 5) + warp_id(); r < n; r += warps) {
-        const float* r0 = s0 + (size_t)r * ld0;
-        const float* r1 = s1 + (size_t)r * ld1 - w0;
-        const float* r2 = s2 + (size_t)r * ld2 - w0 - w1;
-        float* o = out + (size_t)r * ld_out;
-        for (int c = lane_id(); c < ld_out; c += 32) {
-            float v = 0.f;
-            if (c < w0) v = r0[c];
-            else if (c < w0 + w1) v = r1[c];
-            else if (c < w0 + w1 + w2) v = r2[c];
-            o[c] = v;
+    // flat element index over a block's row range: fully coalesced stores, 4 independent loads in flight per thread
+    constexpr int U = 4;
+    const int rows_per_block = (n + gridDim.x - 1) / gridDim.x;
+    const int r_beg = blockIdx.x * rows_per_block, r_end = min(n, r_beg + rows_per_block);
+    const unsigned total = (unsigned)max(r_end - r_beg, 0) * (unsigned)ld_out;      // < 2^31: blocks cover few rows
+    const float* b0 = s0 + (size_t)r_beg * ld0;
+    const float* b1 = s1 + (size_t)r_beg * ld1;
+    const float* b2 = s2 + (size_t)r_beg * ld2;
+    float* o = out + (size_t)r_beg * ld_out;
+    for (unsigned e0 = threadIdx.x; e0 < total; e0 += U * blockDim.x) {
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned e = e0 + u * blockDim.x;
+            v[u] = 0.f;
+            if (e < total) {
+                const unsigned r = e / (unsigned)ld_out, c = e - r * (unsigned)ld_out;
+                if ((int)c < w0) v[u] = b0[(size_t)r * ld0 + c];
+                else if ((int)c < w0 + w1) v[u] = b1[(size_t)r * ld1 + (c - w0)];
+                else if ((int)c < w0 + w1 + w2) v[u] = b2[(size_t)r * ld2 + (c - w0 - w1)];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned e = e0 + u * blockDim.x;
+            if (e < total) o[e] = v[u];
         }
     }
 }
@@ -294,7 +307,7 @@ extern "C" int mrb_concat_cols(const float* s0, int w0, int ld0, const float* s1
     MRB_REQUIRE(out && s0 && w0 > 0 && (w1 == 0 || s1) && (w2 == 0 || s2), "concat_cols: null pointer");
     MRB_REQUIRE(w1 >= 0 && w2 >= 0 && ld0 >= w0 && ld1 >= w1 && ld2 >= w2 && ld_out >= w0 + w1 + w2, "concat_cols: bad widths");
     if (n <= 0) return MRB_OK;
-    const int blocks = (int)min((long long)16 * kNumSMs, ceil_div64(n, 8));
+    const int blocks = (int)min((long long)16 * kNumSMs, ceil_div64(n, 4));      // >= 4 rows per block
     k_concat_cols<<<blocks, 256, 0, (cudaStream_t)stream_>>>(s0, w0, ld0, s1, w1, ld1, s2, w2, ld2, n, out, ld_out);
     return check_launch("concat_cols");
 }
