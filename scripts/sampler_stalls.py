@@ -1,0 +1,40 @@
+"""Does the background `nvidia-smi -lms` clock sampler stall the timed steps?  60 bench steps per sampler setting."""
+import sys, os, time, subprocess, shutil, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+from meshrcnn_b200.layers import Cubify
+from meshrcnn_b200.mesh_sampling import normalize_mesh
+from meshrcnn_b200.pipeline import MeshTargets, RefinementHead, weighted_loss
+from meshrcnn_b200.sharding import FlatGradBucket
+dev = torch.device("cuda", 0)
+B = 32
+vox_h, fmap_h, gt_vox_h = bench.make_inputs(B, 0)
+sizes = [(224, 224)] * B
+torch.manual_seed(1)
+head = RefinementHead("pix3d", cubify_threshold=0.2).to(dev).train()
+bucket = FlatGradBucket(head.parameters())
+gv, gvi, gfaces, gfi, _ = Cubify(0.5)(gt_vox_h.to(dev))
+gt = MeshTargets(torch.cat([normalize_mesh(v) for v in gv.split(gvi)]), gfaces, gvi, gfi)
+vox_d = vox_h.to(dev); fmap_d = fmap_h.to(dev).requires_grad_()
+def step():
+    bucket.zero(); fmap_d.grad = None
+    weighted_loss(head(vox_d, fmap_d, sizes, gt)).backward()
+for _ in range(5): step()
+torch.cuda.synchronize()
+import gc; gc.disable()
+R = "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+for name, fields, ms in (("none", None, 0), ("clocks+reasons @200ms", "clocks.sm,clocks.max.sm," + R, 200), ("clocks only @200ms", "clocks.sm,clocks.max.sm", 200),
+                         ("reasons only @200ms", R, 200), ("clocks+reasons @1000ms", "clocks.sm,clocks.max.sm," + R, 1000)):
+    proc = None
+    if fields:
+        proc = subprocess.Popen([shutil.which("nvidia-smi"), "-i", "0", "--query-gpu=" + fields, "--format=csv,noheader,nounits", "-lms", str(ms)],
+                                stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        time.sleep(1.0)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(60)]
+    for a, b in ev:
+        a.record(); step(); b.record()
+    torch.cuda.synchronize()
+    t = sorted(a.elapsed_time(b) for a, b in ev)
+    print("%-26s median %.2f ms  max %.2f  steps > 1.3 x median: %d  mean %.3f" % (name, t[30], t[-1], sum(x > 1.3 * t[30] for x in t), sum(t) / 60))
+    if proc:
+        proc.terminate(); proc.wait()
