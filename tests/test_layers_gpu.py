@@ -286,3 +286,73 @@ def test_shapenet_heads_production_widths_vs_oracle(lib, model):
         if name.startswith("grad"):
             bound = max(bound, 1e-3)
         assert err <= bound, (name, err, ref)
+
+
+def test_concat_cols_matches_torch_cat_with_strided_parts(lib):
+    """``concat_cols`` (16-byte aligned rows, gradient slices as views) vs ``torch.cat`` incl. strided inputs and the
+    GraphConv that consumes the padded view (reference layers.py:160-165,241-252,321-334)."""
+    from meshrcnn_b200 import functional as F_
+    g = torch.Generator().manual_seed(5)
+    n = 777
+    pos = torch.randn(n, 3, generator=g).cuda().requires_grad_()
+    wide = torch.randn(n, 140, generator=g).cuda().requires_grad_()
+    x = wide[:, 5:133]                                   # 128-wide strided view, not 16-byte aligned
+    feat = torch.randn(n, 256, generator=g).cuda().requires_grad_()
+    got = F_.concat_cols([x, pos, feat])
+    want = torch.cat([x, pos, feat], 1)
+    assert got.shape == want.shape and got.stride(0) % 4 == 0 and torch.equal(got, want)
+    w = torch.randn(n, 387, generator=g).cuda()
+    (got * w).sum().backward()
+    gpos, gwide, gfeat = pos.grad.clone(), wide.grad.clone(), feat.grad.clone()
+    pos.grad = wide.grad = feat.grad = None
+    (want * w).sum().backward()
+    assert torch.equal(gpos, pos.grad) and torch.equal(gwide, wide.grad) and torch.equal(gfeat, feat.grad)
+    # GraphConv on the padded view == GraphConv on a contiguous copy
+    adj = torch.stack([torch.arange(n), (torch.arange(n) + 1) % n]).cuda()
+    adj = torch.cat([adj, adj.flip(0)], 1)
+    adj = adj[:, torch.argsort(adj[0] * n + adj[1])]
+    w0, w1 = (torch.randn(387, 128, generator=g) * 0.05).cuda().requires_grad_(), (torch.randn(387, 128, generator=g) * 0.05).cuda().requires_grad_()
+    outs = []
+    for inp in (got.detach().requires_grad_(), want.detach().contiguous().requires_grad_()):
+        w0.grad = w1.grad = None
+        y = F_.graph_conv(inp, adj, w0, w1)
+        y.square().sum().backward()
+        outs.append((y.detach(), inp.grad.clone(), w0.grad.clone(), w1.grad.clone()))
+    for a, b, what in zip(outs[0], outs[1], ("out", "gx", "gw0", "gw1")):
+        close(a, b.cpu(), what=what)
+
+
+def test_overlapped_losses_equal_single_stream(lib):
+    """The per-stage losses issued on the second CUDA stream (pipeline.RefinementHead.overlap_losses) give the same losses
+    and gradients as the single-stream order of the reference (shapenet_model.py:92-95)."""
+    from meshrcnn_b200 import synthetic
+    from meshrcnn_b200.layers import Cubify
+    from meshrcnn_b200.mesh_sampling import normalize_mesh
+    from meshrcnn_b200.pipeline import MeshTargets, RefinementHead, weighted_loss
+    B, n = 3, 2000
+    vox = synthetic.blob_voxels(B, 16, 3).cuda()
+    fmap = synthetic.feature_maps(B, [synthetic.PIX3D_MAP], 3)[0].cuda().requires_grad_()
+    gv, gvi, gf, gfi, _ = Cubify(0.5)(synthetic.blob_voxels(B, 16, 1003).cuda())
+    gt = MeshTargets(torch.cat([normalize_mesh(v) for v in gv.split(gvi)]), gf, gvi, gfi)
+    torch.manual_seed(2)
+    head = RefinementHead("pix3d", cubify_threshold=0.2).cuda().train()
+    rnd = []
+    for s in range(3):
+        u, x2, x1 = synthetic.sampling_randomness(B, 10000, 50 + s)
+        ug, x2g, x1g = synthetic.sampling_randomness(B, 10000, 60 + s)
+        rnd.append(({"u": u.cuda(), "xi2": x2.cuda(), "xi1": x1.cuda()}, {"u": ug.cuda(), "xi2": x2g.cuda(), "xi1": x1g.cuda()}))
+    res = []
+    for overlap in (True, False):
+        head.overlap_losses = overlap
+        head.zero_grad(set_to_none=True)
+        fmap.grad = None
+        losses = head(vox, fmap, [(224, 224)] * B, gt, loss_randomness=rnd)
+        weighted_loss(losses).backward()
+        torch.cuda.synchronize()
+        res.append(({k: float(v) for k, v in losses.items()}, fmap.grad.clone(), [p.grad.clone() for p in head.parameters()]))
+    assert res[0][0].keys() == res[1][0].keys()
+    for k in res[0][0]:
+        assert abs(res[0][0][k] - res[1][0][k]) <= 1e-5 * abs(res[1][0][k]) + 1e-7, (k, res[0][0][k], res[1][0][k])
+    close(res[0][1], res[1][1].cpu(), what="fmap grad")
+    for a, b in zip(res[0][2], res[1][2]):
+        close(a, b.cpu(), what="param grad")
