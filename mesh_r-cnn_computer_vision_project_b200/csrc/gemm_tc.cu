@@ -551,8 +551,9 @@ constexpr int TN_TAIL_MAX = 4;
 
 constexpr int TN_PROD_WARPS = 8;                       // warp w stages vertices [4w, 4w+4) of every chunk = 16-byte k chunk w
 constexpr int TN_THREADS = (TN_PROD_WARPS + 1) * 32;   // producers (also the epilogue) | MMA issuer
-constexpr int TN_PREFETCH = 1;                         // chunks in flight per producer thread (registers)
-
+// NBMAX: 32-column blocks of G a producer thread stages (N <= 32 * NBMAX); PF: chunks in flight per producer thread.  The
+// register file allows two chunks in flight only for N <= 128 (16 + 4 * NBMAX staging registers per chunk, 168 per thread).
+template <int NBMAX, int TN_PREFETCH>
 __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tn(ParamsTN p) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -597,18 +598,18 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tn(ParamsTN p) {
             // of that row.  Loads use clamped, always-valid addresses and are zero-masked at store time, so no instruction
             // of the load phase depends on a loaded value and TN_PREFETCH chunks stay in flight.
             float xa[TN_PREFETCH][16];           // [mb 0..3][t 0..3]
-            float gb[TN_PREFETCH][32];           // [nb 0..7][t 0..3]
+            float gb[TN_PREFETCH][4 * NBMAX];    // [nb][t 0..3]
             // Tail rows (the stage inputs are 128 k + 3 wide: a further 128-row UMMA tile would be 98 % padding and would
             // stage G once more): the producers of tile 0 already hold G[v, j] in registers, so they also load the `tail`
             // extra X columns of their vertices (warp-uniform loads) and keep C[Kin + m, j] partial sums on the CUDA cores.
             const int ntail = (blockIdx.x == 0) ? p.tail : 0;
             float xt[TN_PREFETCH][4 * TN_TAIL_MAX];   // [t 0..3][m]
-            float tacc[TN_TAIL_MAX][8];               // [m][nb]: column j = nb * 32 + lane
+            float tacc[TN_TAIL_MAX][NBMAX];           // [m][nb]: column j = nb * 32 + lane
 #pragma unroll
             for (int m = 0; m < TN_TAIL_MAX; ++m)
 #pragma unroll
-                for (int nb = 0; nb < 8; ++nb) tacc[m][nb] = 0.f;
-            auto load_chunk = [&](int c, float (&x)[16], float (&g)[32], float (&xtail)[4 * TN_TAIL_MAX]) {
+                for (int nb = 0; nb < NBMAX; ++nb) tacc[m][nb] = 0.f;
+            auto load_chunk = [&](int c, float (&x)[16], float (&g)[4 * NBMAX], float (&xtail)[4 * TN_TAIL_MAX]) {
                 const int v0 = c * BK + warp * 4;
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
@@ -620,7 +621,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tn(ParamsTN p) {
                     for (int mb = 0; mb < 4; ++mb)
                         x[mb * 4 + t] = __ldg(p.X + (size_t)v * p.ldx + min(i0 + mb * 32 + lane, p.Kin - 1));
 #pragma unroll
-                    for (int nb = 0; nb < 8; ++nb)
+                    for (int nb = 0; nb < NBMAX; ++nb)
                         if (nb * 32 < NT) g[nb * 4 + t] = __ldg(p.G + (size_t)v * p.ldg + min(nb * 32 + lane, NT - 1));
                 }
             };
@@ -654,7 +655,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tn(ParamsTN p) {
                         for (int mb = 0; mb < 4; ++mb)
                             split_store(a_hi, a_lo, mb * 32 + lane, &xa[d][mb * 4], (i0 + mb * 32 + lane < p.Kin) ? vleft : 0);
 #pragma unroll
-                        for (int nb = 0; nb < 8; ++nb)
+                        for (int nb = 0; nb < NBMAX; ++nb)
                             if (nb * 32 < NT) split_store(b_hi, b_lo, nb * 32 + lane, &gb[d][nb * 4], vleft);
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         __syncwarp();
@@ -666,7 +667,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tn(ParamsTN p) {
                                 for (int m = 0; m < TN_TAIL_MAX; ++m) {
                                     const float xv = (m < ntail && t < vleft) ? xt[d][t * TN_TAIL_MAX + m] : 0.f;
 #pragma unroll
-                                    for (int nb = 0; nb < 8; ++nb)
+                                    for (int nb = 0; nb < NBMAX; ++nb)
                                         if (nb * 32 < NT) tacc[m][nb] = fmaf(xv, gb[d][nb * 4 + t], tacc[m][nb]);
                                 }
                         }
@@ -703,7 +704,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tn(ParamsTN p) {
 #pragma unroll
                 for (int m = 0; m < TN_TAIL_MAX; ++m)
 #pragma unroll
-                    for (int nb = 0; nb < 8; ++nb)
+                    for (int nb = 0; nb < NBMAX; ++nb)
                         if (m < ntail && nb * 32 < NT) red[(warp * TN_TAIL_MAX + m) * 256 + nb * 32 + lane] = tacc[m][nb];
                 asm volatile("bar.sync 1, %0;" ::"r"(TN_PROD_WARPS * 32));
                 for (int e = threadIdx.x; e < ntail * NT; e += TN_PROD_WARPS * 32) {
@@ -828,7 +829,8 @@ extern "C" int mrb_gemm_tc_wgrad(const float* X, int ldx, const float* G, int ld
     if (V == 0) return MRB_OK;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm_tn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_gemm_tn<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tn<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
         if (e != cudaSuccess) {
             set_error("gemm_tc_wgrad: cannot reserve shared memory: %s", cudaGetErrorString(e));
             return MRB_ERR_CUDA;
@@ -845,6 +847,7 @@ extern "C" int mrb_gemm_tc_wgrad(const float* X, int ldx, const float* G, int ld
     int splits = max(1, min(total_chunks, kNumSMs / mtiles));
     p.chunks_per_split = min(ceil_div(total_chunks, splits), 32);    // <= 384 MMAs chained per accumulator (truncating adds)
     splits = ceil_div(total_chunks, p.chunks_per_split);
-    k_gemm_tn<<<dim3(mtiles, splits), TN_THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(p);
+    if (N <= 128) k_gemm_tn<4, 2><<<dim3(mtiles, splits), TN_THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(p);
+    else k_gemm_tn<8, 1><<<dim3(mtiles, splits), TN_THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(p);
     return check_launch("gemm_tc_wgrad");
 }
