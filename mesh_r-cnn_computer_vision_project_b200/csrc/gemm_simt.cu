@@ -97,66 +97,118 @@ __global__ void k_scale_rows(float* __restrict__ C, int M, int N, int ldc, float
 // ---------------------------------------------------------------------------------------------------------
 constexpr int SKINNY = 8;
 
-// C[M x N] = A[M x K] * B[N x K]^T, N <= 8: one warp per row, lanes stride over K, N accumulators, warp reduce
+// C[M x N] = A[M x K] * B[N x K]^T, N <= NACC: one warp per row (coalesced reads of the long rows), lanes stride over K,
+// two rows per warp in flight, NACC accumulators per row, warp reduce
+template <int NACC>
 __global__ void __launch_bounds__(256) k_skinny_nt(int M, int N, int K, const float* __restrict__ A, int lda,
                                                    const float* __restrict__ B, int ldb, float beta, float* __restrict__ C,
                                                    int ldc) {
-    const int m = blockIdx.x * (blockDim.x >> 5) + warp_id();
-    if (m >= M) return;
-    float acc[SKINNY];
+    const int m0 = (blockIdx.x * (blockDim.x >> 5) + warp_id()) * 2;
+    if (m0 >= M) return;
+    const int m1 = min(m0 + 1, M - 1);
+    float acc0[NACC], acc1[NACC];
 #pragma unroll
-    for (int n = 0; n < SKINNY; ++n) acc[n] = 0.f;
+    for (int n = 0; n < NACC; ++n) acc0[n] = acc1[n] = 0.f;
     for (int k = lane_id(); k < K; k += 32) {
-        const float a = A[(size_t)m * lda + k];
+        const float a0 = A[(size_t)m0 * lda + k], a1 = A[(size_t)m1 * lda + k];
 #pragma unroll
-        for (int n = 0; n < SKINNY; ++n)
-            if (n < N) acc[n] = fmaf(a, __ldg(B + (size_t)n * ldb + k), acc[n]);
+        for (int n = 0; n < NACC; ++n)
+            if (n < N) {
+                const float b = __ldg(B + (size_t)n * ldb + k);
+                acc0[n] = fmaf(a0, b, acc0[n]);
+                acc1[n] = fmaf(a1, b, acc1[n]);
+            }
     }
 #pragma unroll
-    for (int n = 0; n < SKINNY; ++n) acc[n] = warp_sum(acc[n]);
+    for (int n = 0; n < NACC; ++n)
+        if (n < N) { acc0[n] = warp_sum(acc0[n]); acc1[n] = warp_sum(acc1[n]); }
     if (lane_id() < N) {
-        float v = 0.f;
+        float v0 = 0.f, v1 = 0.f;
 #pragma unroll
-        for (int n = 0; n < SKINNY; ++n)
-            if (n == lane_id()) v = acc[n];
-        float* c = C + (size_t)m * ldc + lane_id();
-        *c = (beta == 0.f) ? v : fmaf(beta, *c, v);
+        for (int n = 0; n < NACC; ++n)
+            if (n == lane_id()) { v0 = acc0[n]; v1 = acc1[n]; }
+        float* c0 = C + (size_t)m0 * ldc + lane_id();
+        *c0 = (beta == 0.f) ? v0 : fmaf(beta, *c0, v0);
+        if (m0 + 1 < M) {
+            float* c1 = C + (size_t)(m0 + 1) * ldc + lane_id();
+            *c1 = (beta == 0.f) ? v1 : fmaf(beta, *c1, v1);
+        }
     }
 }
 
-// C[M x N] = A[M x K] * B[K x N], K <= 8: one thread per output element
+// C[M x N] = A[M x K] * B[K x N], K <= 8: one warp per row, lanes stride over the N columns (coalesced stores, the K values
+// of the row are broadcast loads, B comes from L1)
 __global__ void __launch_bounds__(256) k_skinny_k(int M, int N, int K, const float* __restrict__ A, int lda,
                                                   const float* __restrict__ B, int ldb, float beta, float* __restrict__ C,
                                                   int ldc) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)M * N) return;
-    const int m = (int)(t / N), n = (int)(t % N);
-    float acc = 0.f;
+    const int m = blockIdx.x * (blockDim.x >> 5) + warp_id();
+    if (m >= M) return;
+    float a[SKINNY];
 #pragma unroll
-    for (int k = 0; k < SKINNY; ++k)
-        if (k < K) acc = fmaf(A[(size_t)m * lda + k], __ldg(B + (size_t)k * ldb + n), acc);
-    float* c = C + (size_t)m * ldc + n;
-    *c = (beta == 0.f) ? acc : fmaf(beta, *c, acc);
+    for (int k = 0; k < SKINNY; ++k) a[k] = (k < K) ? A[(size_t)m * lda + k] : 0.f;
+    for (int n = lane_id(); n < N; n += 32) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < SKINNY; ++k)
+            if (k < K) acc = fmaf(a[k], __ldg(B + (size_t)k * ldb + n), acc);
+        float* c = C + (size_t)m * ldc + n;
+        *c = (beta == 0.f) ? acc : fmaf(beta, *c, acc);
+    }
 }
 
-// C[M x N] += A[K x M]^T * B[K x N], M <= 8 (C pre-scaled by beta): blocks own chunks of the long K dimension
+// C[M x N] += A[K x M]^T * B[K x N], M <= MACC (C pre-scaled by beta): a block owns a chunk of the long K dimension; warp w
+// takes rows w, w + 8, ... of the chunk, lanes stride over the N <= 256 columns (coalesced), the 8 warps' partial sums are
+// combined in shared memory and added to C with one atomic per element and block.
+template <int MACC>
 __global__ void __launch_bounds__(256) k_skinny_tn(int M, int N, int K, const float* __restrict__ A, int lda,
                                                    const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
                                                    int rows_per_block) {
+    constexpr int JMAX = 8;                                // N <= 256
+    __shared__ float red[8][MACC][32 * JMAX / 4 + 1];      // reused per column quarter (see below)
     const int k0 = blockIdx.x * rows_per_block, k1 = min(K, k0 + rows_per_block);
-    for (int n = threadIdx.x; n < N; n += blockDim.x) {
-        float acc[SKINNY];
+    const int nj = (N + 31) >> 5;
+    float acc[MACC][JMAX];
 #pragma unroll
-        for (int m = 0; m < SKINNY; ++m) acc[m] = 0.f;
-        for (int k = k0; k < k1; ++k) {
-            const float b = B[(size_t)k * ldb + n];
+    for (int m = 0; m < MACC; ++m)
 #pragma unroll
-            for (int m = 0; m < SKINNY; ++m)
-                if (m < M) acc[m] = fmaf(__ldg(A + (size_t)k * lda + m), b, acc[m]);
+        for (int j = 0; j < JMAX; ++j) acc[m][j] = 0.f;
+    for (int k = k0 + warp_id(); k < k1; k += 8) {
+        float a[MACC];
+#pragma unroll
+        for (int m = 0; m < MACC; ++m) a[m] = (m < M) ? __ldg(A + (size_t)k * lda + m) : 0.f;
+#pragma unroll
+        for (int j = 0; j < JMAX; ++j) {
+            const int n = j * 32 + lane_id();
+            if (j < nj && n < N) {
+                const float b = B[(size_t)k * ldb + n];
+#pragma unroll
+                for (int m = 0; m < MACC; ++m) acc[m][j] = fmaf(a[m], b, acc[m][j]);
+            }
         }
+    }
+    // combine the 8 warps, two column blocks (64 columns) at a time
+    for (int jb = 0; jb < nj; jb += 2) {
+        __syncthreads();
 #pragma unroll
-        for (int m = 0; m < SKINNY; ++m)
-            if (m < M) atomicAdd(C + (size_t)m * ldc + n, acc[m]);
+        for (int m = 0; m < MACC; ++m)
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                float v = 0.f;
+#pragma unroll
+                for (int j = 0; j < JMAX; ++j)
+                    if (j == jb + jj) v = acc[m][j];
+                red[warp_id()][m][jj * 32 + lane_id()] = v;
+            }
+        __syncthreads();
+        for (int e = threadIdx.x; e < MACC * 64; e += blockDim.x) {
+            const int m = e / 64, c = e % 64, n = jb * 32 + c;
+            if (m < M && n < N) {
+                float v = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) v += red[w][m][c];
+                atomicAdd(C + (size_t)m * ldc + n, v);
+            }
+        }
     }
 }
 
@@ -173,17 +225,19 @@ extern "C" int mrb_sgemm(int transA, int transB, int M, int N, int K, const floa
     if (M == 0 || N == 0) return MRB_OK;
     cudaStream_t s = (cudaStream_t)stream_;
     if (K > 0 && !transA && transB && N <= SKINNY) {
-        k_skinny_nt<<<ceil_div(M, 8), 256, 0, s>>>(M, N, K, A, lda, B, ldb, beta, C, ldc);
+        if (N <= 4) k_skinny_nt<4><<<ceil_div(M, 16), 256, 0, s>>>(M, N, K, A, lda, B, ldb, beta, C, ldc);
+        else k_skinny_nt<SKINNY><<<ceil_div(M, 16), 256, 0, s>>>(M, N, K, A, lda, B, ldb, beta, C, ldc);
         return check_launch("sgemm");
     }
     if (K > 0 && !transA && !transB && K <= SKINNY) {
-        k_skinny_k<<<(unsigned)ceil_div64((long long)M * N, 256), 256, 0, s>>>(M, N, K, A, lda, B, ldb, beta, C, ldc);
+        k_skinny_k<<<ceil_div(M, 8), 256, 0, s>>>(M, N, K, A, lda, B, ldb, beta, C, ldc);
         return check_launch("sgemm");
     }
-    if (K > 0 && transA && !transB && M <= SKINNY) {
+    if (K > 0 && transA && !transB && M <= SKINNY && N <= 256) {
         k_scale_rows<<<(unsigned)ceil_div64((long long)M * N, 256), 256, 0, s>>>(C, M, N, ldc, beta);
         const int rpb = max(64, ceil_div(K, 4 * kNumSMs));
-        k_skinny_tn<<<ceil_div(K, rpb), 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, rpb);
+        if (M <= 4) k_skinny_tn<4><<<ceil_div(K, rpb), 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, rpb);
+        else k_skinny_tn<SKINNY><<<ceil_div(K, rpb), 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, rpb);
         return check_launch("sgemm");
     }
     const int gx = ceil_div(N, BN), gy = ceil_div(M, BM);
