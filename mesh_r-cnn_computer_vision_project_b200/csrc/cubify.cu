@@ -163,12 +163,22 @@ __global__ void __launch_bounds__(1024) k_scan(Dims d, Workspace ws, long long* 
     else if (blockIdx.x == 1) { arr = ws.vertOff; n = d.B * d.nchL; }
     else { arr = ws.edgeOff; n = d.B * d.nchL; }
     int carry = 0;
-    for (int base = 0; base < n; base += 1024) {
-        const int i = base + threadIdx.x;
-        const int v = (i < n) ? arr[i] : 0;
+    constexpr int PER = 8;                       // consecutive elements per thread: 8192 per block-scan round
+    for (int base = 0; base < n; base += 1024 * PER) {
+        const int i0 = base + threadIdx.x * PER;
+        int vals[PER], sum = 0;
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            vals[u] = (i0 + u < n) ? arr[i0 + u] : 0;
+            sum += vals[u];
+        }
         int total;
-        const int ex = block_exclusive_scan(v, scratch, &total);
-        if (i < n) arr[i] = carry + ex;
+        int run = carry + block_exclusive_scan(sum, scratch, &total);
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            if (i0 + u < n) arr[i0 + u] = run;
+            run += vals[u];
+        }
         carry += total;
         __syncthreads();
     }
@@ -269,11 +279,12 @@ __global__ void __launch_bounds__(ADJ_BLOCK) k_emit_adj(Dims d, Workspace ws, in
 }
 
 // pass 2c: faces in (b, dir, z, y, x) order, two triangles (c0,c1,c2),(c0,c2,c3) per quad, per-mesh local ids.
-// Per direction the block's quads are one contiguous output range: staged in shared memory, written coalesced.
+// A quad is 6 int64 = 48 contiguous bytes and consecutive flagged lanes write consecutive quads, so every thread stores its
+// quad straight from registers as three 16-byte vectors (a warp covers up to 1.5 KB of contiguous output); one barrier for
+// the per-warp offsets of all six directions.
 __global__ void __launch_bounds__(CH) k_emit_faces(Dims d, Workspace ws, const long long* __restrict__ meta,
                                                    long long* __restrict__ faces) {
     __shared__ int wtot[6][CH / 32];
-    __shared__ int32_t stage[CH * 6];
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int v = chunk * CH + threadIdx.x;
     const unsigned f = (v < d.nvox) ? ws.ff[(size_t)b * d.nvox + v] : 0u;
@@ -285,33 +296,26 @@ __global__ void __launch_bounds__(CH) k_emit_faces(Dims d, Workspace ws, const l
         if (lane_id() == 0) wtot[k][warp_id()] = __popc(bal);
     }
     __syncthreads();
+    if (f == 0u) return;
     const int x = v % d.X, y = (v / d.X) % d.Y, z = v / (d.X * d.Y);
     const int voff = (int)meta[4 + 2 * d.B + b];
     const int32_t* rk = ws.rank + (size_t)b * d.nlat;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-        int total = 0, before = 0;
-        for (int w = 0; w < CH / 32; ++w) {
-            const int t = wtot[k][w];
-            before += (w < warp_id()) ? t : 0;
-            total += t;
-        }
-        if (total == 0) continue;                 // block-uniform
-        if ((f >> k) & 1u) {
-            int c[4];
+        if (!((f >> k) & 1u)) continue;
+        int before = 0;
+        for (int w = 0; w < warp_id(); ++w) before += wtot[k][w];
+        long long c[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int lz = z + kCorner[k][j][0], ly = y + kCorner[k][j][1], lx = x + kCorner[k][j][2];
-                c[j] = rk[((size_t)lz * d.LY + ly) * d.LX + lx] - voff;
-            }
-            int32_t* o = stage + (before + pre[k]) * 6;
-            o[0] = c[0]; o[1] = c[1]; o[2] = c[2]; o[3] = c[0]; o[4] = c[2]; o[5] = c[3];
+        for (int j = 0; j < 4; ++j) {
+            const int lz = z + kCorner[k][j][0], ly = y + kCorner[k][j][1], lx = x + kCorner[k][j][2];
+            c[j] = rk[((size_t)lz * d.LY + ly) * d.LX + lx] - voff;
         }
-        __syncthreads();
-        const long long q0 = ws.faceOff[((size_t)b * 6 + k) * d.nchF + chunk];
-        long long* out = faces + q0 * 6;
-        for (int t = threadIdx.x; t < total * 6; t += CH) out[t] = stage[t];
-        __syncthreads();
+        const long long q = ws.faceOff[((size_t)b * 6 + k) * d.nchF + chunk] + before + pre[k];
+        longlong2* o = reinterpret_cast<longlong2*>(faces + q * 6);          // 48-byte quads: 16-byte aligned
+        o[0] = make_longlong2(c[0], c[1]);
+        o[1] = make_longlong2(c[2], c[0]);
+        o[2] = make_longlong2(c[2], c[3]);
     }
 }
 
