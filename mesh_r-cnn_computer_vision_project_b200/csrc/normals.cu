@@ -67,34 +67,43 @@ __device__ void eigh3(const double a[6], double w[3], double V[3][3]) {
     // canonical signs
     if (V[2][0] < 0.0) for (int r = 0; r < 3; ++r) V[r][0] = -V[r][0];
     {
-        int big = 0;
-        if (fabs(V[1][1]) > fabs(V[big][1])) big = 1;
-        if (fabs(V[2][1]) > fabs(V[big][1])) big = 2;
-        if (V[big][1] < 0.0) for (int r = 0; r < 3; ++r) V[r][1] = -V[r][1];
+        double vb = V[0][1];                                    // largest-|.| component of column 1 (first wins ties)
+        if (fabs(V[1][1]) > fabs(vb)) vb = V[1][1];
+        if (fabs(V[2][1]) > fabs(vb)) vb = V[2][1];
+        if (vb < 0.0) for (int r = 0; r < 3; ++r) V[r][1] = -V[r][1];
     }
     const double det = V[0][0] * (V[1][1] * V[2][2] - V[1][2] * V[2][1]) - V[0][1] * (V[1][0] * V[2][2] - V[1][2] * V[2][0]) +
                        V[0][2] * (V[1][0] * V[2][1] - V[1][1] * V[2][0]);
     if (det < 0.0) for (int r = 0; r < 3; ++r) V[r][2] = -V[r][2];
 }
 
-// gathers the k neighbours of point (batch, p) from pt, returns centred rows Y and the scatter matrix
-__device__ __forceinline__ void neighbourhood(const float* __restrict__ pt, const int32_t* __restrict__ nn, int k,
+// gathers the k neighbours of point (batch, p) from pt, returns centred rows Y and the scatter matrix.
+// KT > 0: k is the compile-time constant KT, the loops unroll and Y stays in registers (with a run-time k the dynamically
+// indexed Y lives in local memory and the kernel is bound by it); KT = 0: generic k <= KMAX.
+template <int KT>
+__device__ __forceinline__ void neighbourhood(const float* __restrict__ pt, const int32_t* __restrict__ nn, int k_rt,
                                               double Y[KMAX][3], double S[6]) {
+    const int k = KT > 0 ? KT : k_rt;
     double m[3] = {0, 0, 0};
-    for (int j = 0; j < k; ++j) {
+#pragma unroll
+    for (int j = 0; j < (KT > 0 ? KT : KMAX); ++j) {
+        if (j >= k) break;
         const float* r = pt + 3 * (size_t)nn[j];
         Y[j][0] = r[0]; Y[j][1] = r[1]; Y[j][2] = r[2];
         m[0] += Y[j][0]; m[1] += Y[j][1]; m[2] += Y[j][2];
     }
     m[0] /= k; m[1] /= k; m[2] /= k;
     for (int c = 0; c < 6; ++c) S[c] = 0.0;
-    for (int j = 0; j < k; ++j) {
+#pragma unroll
+    for (int j = 0; j < (KT > 0 ? KT : KMAX); ++j) {
+        if (j >= k) break;
         const double y0 = Y[j][0] - m[0], y1 = Y[j][1] - m[1], y2 = Y[j][2] - m[2];
         Y[j][0] = y0; Y[j][1] = y1; Y[j][2] = y2;
         S[0] += y0 * y0; S[1] += y0 * y1; S[2] += y0 * y2; S[3] += y1 * y1; S[4] += y1 * y2; S[5] += y2 * y2;
     }
 }
 
+template <int KT>
 __global__ void __launch_bounds__(128) k_normals_fwd(const float* __restrict__ pt, const int32_t* __restrict__ knn, int P,
                                                      int k, float* __restrict__ normals) {
     const int batch = blockIdx.y;
@@ -102,7 +111,7 @@ __global__ void __launch_bounds__(128) k_normals_fwd(const float* __restrict__ p
     if (p >= P) return;
     const size_t o = (size_t)batch * P + p;
     double Y[KMAX][3], S[6], w[3], V[3][3];
-    neighbourhood(pt + (size_t)batch * P * 3, knn + o * k, k, Y, S);
+    neighbourhood<KT>(pt + (size_t)batch * P * 3, knn + o * k, k, Y, S);
     eigh3(S, w, V);
     normals[3 * o] = (float)V[0][0];
     normals[3 * o + 1] = (float)V[0][1];
@@ -111,6 +120,7 @@ __global__ void __launch_bounds__(128) k_normals_fwd(const float* __restrict__ p
 
 // gn -> gpt (atomic scatter to the gathered rows):  n_j = V[0][j]
 //   K_ij = V[0][i] gn_j / (w_j - w_i) (i != j),  gS = V K V^T,  gY = Y (gS + gS^T)
+template <int KT>
 __global__ void __launch_bounds__(128) k_normals_bwd(const float* __restrict__ pt, const int32_t* __restrict__ knn, int P,
                                                      int k, const float* __restrict__ gn, float* __restrict__ gpt) {
     const int batch = blockIdx.y;
@@ -121,7 +131,7 @@ __global__ void __launch_bounds__(128) k_normals_bwd(const float* __restrict__ p
     if (g[0] == 0.0 && g[1] == 0.0 && g[2] == 0.0) return;
     double Y[KMAX][3], S[6], w[3], V[3][3];
     const int32_t* nn = knn + o * k;
-    neighbourhood(pt + (size_t)batch * P * 3, nn, k, Y, S);
+    neighbourhood<KT>(pt + (size_t)batch * P * 3, nn, k, Y, S);
     eigh3(S, w, V);
     double Kf[3][3];
     const double tiny = 1e-14 * (fabs(w[0]) + fabs(w[1]) + fabs(w[2])) + 1e-300;
@@ -138,7 +148,9 @@ __global__ void __launch_bounds__(128) k_normals_bwd(const float* __restrict__ p
     for (int i = 0; i < 3; ++i)
         for (int j = i; j < 3; ++j) { const double s = G[i][j] + G[j][i]; G[i][j] = s; G[j][i] = s; }
     float* gb = gpt + (size_t)batch * P * 3;
-    for (int j = 0; j < k; ++j) {
+#pragma unroll
+    for (int j = 0; j < (KT > 0 ? KT : KMAX); ++j) {
+        if (j >= (KT > 0 ? KT : k)) break;
         const size_t r = 3 * (size_t)nn[j];
         atomicAdd(gb + r, (float)(Y[j][0] * G[0][0] + Y[j][1] * G[1][0] + Y[j][2] * G[2][0]));
         atomicAdd(gb + r + 1, (float)(Y[j][0] * G[0][1] + Y[j][1] * G[1][1] + Y[j][2] * G[2][1]));
@@ -239,7 +251,9 @@ extern "C" int mrb_normals_fwd(const float* pt, const int32_t* knn, int B, int P
     MRB_REQUIRE(pt && knn && normals_out, "normals_fwd: null pointer");
     MRB_REQUIRE(k >= 1 && k <= KMAX, "normals_fwd: k must be in [1, %d]", KMAX);
     if (B == 0 || P == 0) return MRB_OK;
-    k_normals_fwd<<<dim3(ceil_div(P, 128), B), 128, 0, (cudaStream_t)stream_>>>(pt, knn, P, k, normals_out);
+    const dim3 grid(ceil_div(P, 128), B);
+    if (k == 10) k_normals_fwd<10><<<grid, 128, 0, (cudaStream_t)stream_>>>(pt, knn, P, k, normals_out);       // the reference default
+    else k_normals_fwd<0><<<grid, 128, 0, (cudaStream_t)stream_>>>(pt, knn, P, k, normals_out);
     return check_launch("normals_fwd");
 }
 
@@ -248,7 +262,9 @@ extern "C" int mrb_normals_bwd(const float* pt, const int32_t* knn, int B, int P
     MRB_REQUIRE(pt && knn && gn && gpt, "normals_bwd: null pointer");
     MRB_REQUIRE(k >= 1 && k <= KMAX, "normals_bwd: k must be in [1, %d]", KMAX);
     if (B == 0 || P == 0) return MRB_OK;
-    k_normals_bwd<<<dim3(ceil_div(P, 128), B), 128, 0, (cudaStream_t)stream_>>>(pt, knn, P, k, gn, gpt);
+    const dim3 grid(ceil_div(P, 128), B);
+    if (k == 10) k_normals_bwd<10><<<grid, 128, 0, (cudaStream_t)stream_>>>(pt, knn, P, k, gn, gpt);
+    else k_normals_bwd<0><<<grid, 128, 0, (cudaStream_t)stream_>>>(pt, knn, P, k, gn, gpt);
     return check_launch("normals_bwd");
 }
 

@@ -23,18 +23,20 @@ for _ in range(5): step()
 torch.cuda.synchronize()
 import gc; gc.disable()
 R = "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-for name, fields, ms in (("none", None, 0), ("clocks+reasons @200ms", "clocks.sm,clocks.max.sm," + R, 200), ("clocks only @200ms", "clocks.sm,clocks.max.sm", 200),
-                         ("reasons only @200ms", R, 200), ("clocks+reasons @1000ms", "clocks.sm,clocks.max.sm," + R, 1000)):
+NSTEP = int(sys.argv[1]) if len(sys.argv) > 1 else 60
+for name, fields, ms in (("none", None, 0), ("clocks+reasons @200ms", "clocks.sm,clocks.max.sm," + R, 200), ("none again", None, 0),
+                         ("clocks only @200ms", "clocks.sm,clocks.max.sm", 200), ("clocks+reasons @50ms", "clocks.sm,clocks.max.sm," + R, 50)):
     proc = None
     if fields:
         proc = subprocess.Popen([shutil.which("nvidia-smi"), "-i", "0", "--query-gpu=" + fields, "--format=csv,noheader,nounits", "-lms", str(ms)],
                                 stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         time.sleep(1.0)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(60)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(NSTEP)]
     for a, b in ev:
         a.record(); step(); b.record()
     torch.cuda.synchronize()
     t = sorted(a.elapsed_time(b) for a, b in ev)
-    print("%-26s median %.2f ms  max %.2f  steps > 1.3 x median: %d  mean %.3f" % (name, t[30], t[-1], sum(x > 1.3 * t[30] for x in t), sum(t) / 60))
+    med = t[len(t) // 2]
+    print("%-26s median %.2f ms  max %.2f  steps > 1.3 x median: %d  mean %.3f  worst5 %s" % (name, med, t[-1], sum(x > 1.3 * med for x in t), sum(t) / len(t), ["%.1f" % x for x in t[-5:]]))
     if proc:
         proc.terminate(); proc.wait()
