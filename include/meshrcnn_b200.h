@@ -134,7 +134,7 @@ int mrb_vert_align_bwd(const float* gout, int ld_g, int n_img, int C, int Hm, in
  *                         weights (1-sqrt(xi1), (1-xi2)sqrt(xi1), xi2 sqrt(xi1)); u/xi2/xi1 NULL => Philox(seed).
  *                         Outputs: raw points, global face id, weights (saved for backward), normalised cloud and
  *                         per-cloud stats (8 doubles: mean[3], factor, argmax row or -1).
- *   mrb_sample_points_bwd gcloud -> gverts (accumulated with atomics; caller zero-fills)
+ *   mrb_sample_points_bwd gcloud -> gverts (accumulated with atomics; caller zero-fills); scratch: 4 * B doubles
  */
 int mrb_face_areas(const float* verts, const long long* faces, const int32_t* v_off, const int32_t* f_off, int B,
                    int max_faces, float* areas, void* stream);
@@ -147,7 +147,7 @@ int mrb_sample_points_fwd(const float* verts, const long long* faces, const int3
 int mrb_normalize_cloud_fwd(const float* raw, int B, int n, float* cloud, double* stats, void* stream);
 int mrb_sample_points_bwd(const float* gcloud, const float* cloud, const double* stats, const int32_t* fidx,
                           const float* w, const long long* faces, const int32_t* v_off, int B, int n, float* gverts,
-                          void* stream);
+                          double* scratch /* 4 * B doubles */, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Chamfer / k-NN -- replaces batched_point2point_distance (cross branch), batched_chamfer_distance and the topk of

@@ -189,54 +189,60 @@ __global__ void __launch_bounds__(1024) k_normalize(const float* __restrict__ ra
     }
 }
 
-// backward of normalise + barycentric combination: scatters into gverts (atomics). One block per cloud.
-__global__ void __launch_bounds__(1024) k_sample_bwd(const float* __restrict__ gy, const float* __restrict__ y,
-                                                     const double* __restrict__ stats, const int32_t* __restrict__ fidx,
-                                                     const float* __restrict__ w, const long long* __restrict__ faces,
-                                                     const int32_t* __restrict__ v_off, int n,
-                                                     float* __restrict__ gverts) {
+// backward of normalise + barycentric combination, two launches over the whole batch:
+//   k_sample_bwd_sums : tot[b] = (sum_i g_i, sum_i g_i . y_i)  -- 8 blocks per cloud, fp64 atomics into tot (zeroed)
+//   k_sample_bwd      : one thread per sampled point scatters into gverts (atomics)
+constexpr int BWD_SPLIT = 8;
+__global__ void __launch_bounds__(256) k_sample_bwd_sums(const float* __restrict__ gy, const float* __restrict__ y, int n,
+                                                         double* __restrict__ tot) {
     __shared__ double sd[33];
-    __shared__ double s_tot[4];
-    const int b = blockIdx.x;
+    const int b = blockIdx.y;
     const size_t base = (size_t)b * n;
-    const double f = stats[8 * (size_t)b + 3];
-    const int am = (int)stats[8 * (size_t)b + 4];
-    // s = sum_i g_i . y_i ; G = sum_i g_i
     double acc[4] = {0, 0, 0, 0};
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double g0 = gy[3 * (base + i)], g1 = gy[3 * (base + i) + 1], g2 = gy[3 * (base + i) + 2];
         acc[0] += g0; acc[1] += g1; acc[2] += g2;
         acc[3] += g0 * y[3 * (base + i)] + g1 * y[3 * (base + i) + 1] + g2 * y[3 * (base + i) + 2];
     }
     for (int d = 0; d < 4; ++d) {
         const double t = block_sum<double>(acc[d], sd);
-        if (threadIdx.x == 0) s_tot[d] = t;
+        if (threadIdx.x == 0) atomicAdd(tot + 4 * (size_t)b + d, t);
         __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(256) k_sample_bwd(const float* __restrict__ gy, const float* __restrict__ y,
+                                                    const double* __restrict__ stats, const double* __restrict__ tot,
+                                                    const int32_t* __restrict__ fidx, const float* __restrict__ w,
+                                                    const long long* __restrict__ faces, const int32_t* __restrict__ v_off, int n,
+                                                    float* __restrict__ gverts) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t base = (size_t)b * n;
+    const double f = stats[8 * (size_t)b + 3];
+    const int am = (int)stats[8 * (size_t)b + 4];
     // gc_i = g_i / f  (+ for i == argmax:  -(s / f) * y_m);   gx_i = gc_i - mean_j gc_j
     double extra[3] = {0, 0, 0};
     if (am >= 0) {
-        const double k = -s_tot[3] / f;
+        const double k = -tot[4 * (size_t)b + 3] / f;
         for (int d = 0; d < 3; ++d) extra[d] = k * (double)y[3 * (base + am) + d];
     }
-    double gmean[3];
-    for (int d = 0; d < 3; ++d) gmean[d] = (s_tot[d] / f + extra[d]) / (double)n;
+    float gx[3];
+    for (int d = 0; d < 3; ++d) {
+        const double gmean = (tot[4 * (size_t)b + d] / f + extra[d]) / (double)n;
+        double g = (double)gy[3 * (base + i) + d] / f - gmean;
+        if (i == am) g += extra[d];
+        gx[d] = (float)g;
+    }
     const long long o = v_off[b];
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        float gx[3];
-        for (int d = 0; d < 3; ++d) {
-            double g = (double)gy[3 * (base + i) + d] / f - gmean[d];
-            if (i == am) g += extra[d];
-            gx[d] = (float)g;
-        }
-        const int fi = fidx[base + i];
-        for (int c = 0; c < 3; ++c) {
-            const long long v = faces[3 * (size_t)fi + c] + o;
-            const float wc = w[3 * (base + i) + c];
-            atomicAdd(gverts + 3 * v, wc * gx[0]);
-            atomicAdd(gverts + 3 * v + 1, wc * gx[1]);
-            atomicAdd(gverts + 3 * v + 2, wc * gx[2]);
-        }
+    const int fi = fidx[base + i];
+    for (int c = 0; c < 3; ++c) {
+        const long long v = faces[3 * (size_t)fi + c] + o;
+        const float wc = w[3 * (base + i) + c];
+        atomicAdd(gverts + 3 * v, wc * gx[0]);
+        atomicAdd(gverts + 3 * v + 1, wc * gx[1]);
+        atomicAdd(gverts + 3 * v + 2, wc * gx[2]);
     }
 }
 
@@ -291,9 +297,13 @@ extern "C" int mrb_normalize_cloud_fwd(const float* raw, int B, int n, float* cl
 
 extern "C" int mrb_sample_points_bwd(const float* gcloud, const float* cloud, const double* stats, const int32_t* fidx,
                                      const float* w, const long long* faces, const int32_t* v_off, int B, int n,
-                                     float* gverts, void* stream_) {
-    MRB_REQUIRE(gcloud && cloud && stats && fidx && w && faces && v_off && gverts, "sample_points_bwd: null pointer");
+                                     float* gverts, double* scratch, void* stream_) {
+    MRB_REQUIRE(gcloud && cloud && stats && fidx && w && faces && v_off && gverts && scratch, "sample_points_bwd: null pointer");
+    MRB_REQUIRE(B <= 65535, "sample_points_bwd: batch too large");
     if (B == 0 || n == 0) return MRB_OK;
-    k_sample_bwd<<<B, 1024, 0, (cudaStream_t)stream_>>>(gcloud, cloud, stats, fidx, w, faces, v_off, n, gverts);
+    cudaStream_t s = (cudaStream_t)stream_;
+    cudaMemsetAsync(scratch, 0, sizeof(double) * 4 * (size_t)B, s);
+    k_sample_bwd_sums<<<dim3(BWD_SPLIT, B), 256, 0, s>>>(gcloud, cloud, n, scratch);
+    k_sample_bwd<<<dim3(ceil_div(n, 256), B), 256, 0, s>>>(gcloud, cloud, stats, scratch, fidx, w, faces, v_off, n, gverts);
     return check_launch("sample_points_bwd");
 }

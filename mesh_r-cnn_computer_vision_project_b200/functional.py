@@ -494,8 +494,9 @@ class _Sample(torch.autograd.Function):
         cloud, stats, fidx, w, f, v_off = ctx.saved_tensors
         B, n, vshape = ctx.dims
         gverts = torch.zeros(vshape, dtype=torch.float32, device=cloud.device)
+        scratch = torch.empty(4 * B, dtype=torch.float64, device=cloud.device)
         _lib.call("mrb_sample_points_bwd", _lib.ptr(_f32c(gcloud)), _lib.ptr(cloud), _lib.ptr(stats), _lib.ptr(fidx),
-                  _lib.ptr(w), _lib.ptr(f), _lib.ptr(v_off), B, n, _lib.ptr(gverts))
+                  _lib.ptr(w), _lib.ptr(f), _lib.ptr(v_off), B, n, _lib.ptr(gverts), _lib.ptr(scratch))
         return (gverts,) + (None,) * 11
 
 
