@@ -100,6 +100,11 @@ int mrb_sgemm(int transA, int transB, int M, int N, int K, const float* A, int l
 long long mrb_gemm_tc_image_bytes(int K, int N);
 int mrb_gemm_tc_pack(const float* src0, const float* src1, long long stride_k, long long stride_n, int split_axis,
                      int split_at, int K, int N, void* image, void* stream);
+/* Both weight images of one GraphConv (w0, w1: K x D row-major) in a single launch: image_fwd = operand of
+ * x @ [W0 | W1] (mrb_gemm_tc_image_bytes(K, 2D) bytes), image_bwd = operand of [gz | A^T gz] @ [W0 | W1]^T
+ * (mrb_gemm_tc_image_bytes(2D, K) bytes). */
+int mrb_gemm_tc_pack_graphconv(const float* w0, const float* w1, int K, int D, void* image_fwd, void* image_bwd,
+                               void* stream);
 int mrb_gemm_tc(const float* A, int lda, int M, int K, const void* image, int N, float* C, int ldc, void* stream);
 /* Weight gradients on the same tensor-core path: C[Kin x N] += X^T (V x Kin) * G (V x N), reduced over the V vertices
  * (split over CTAs, fp32 vector reductions into C -- the caller zero-fills C).  Columns [0, n_split) go to C0 and

@@ -470,9 +470,8 @@ struct PackParams {
     unsigned char* image;
 };
 
-__global__ void k_pack_b(PackParams p) {
+__device__ __forceinline__ void pack_element(const PackParams& p, long long t) {
     const long long total = (long long)p.ntiles * p.nchunks * p.NT * BK;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
     const int kl = (int)(t % BK);
     const int nl = (int)((t / BK) % p.NT);
@@ -493,6 +492,15 @@ __global__ void k_pack_b(PackParams p) {
     const int off = swz(nl, kl);
     *reinterpret_cast<float*>(base + off) = hi;
     *reinterpret_cast<float*>(base + tile_bytes + off) = lo;
+}
+
+__global__ void k_pack_b(PackParams p) { pack_element(p, (long long)blockIdx.x * blockDim.x + threadIdx.x); }
+
+// two images in one launch (a GraphConv's forward operand [W0 | W1] and the transposed operand of its input gradient)
+__global__ void k_pack_b2(PackParams a, PackParams b, long long total_a) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < total_a) pack_element(a, t);
+    else pack_element(b, t - total_a);
 }
 
 struct Plan {
@@ -772,6 +780,22 @@ extern "C" int mrb_gemm_tc_pack(const float* src0, const float* src1, long long 
     const long long total = (long long)pl.ntiles * pl.nchunks * pl.NT * BK;
     k_pack_b<<<(unsigned)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream_>>>(p);
     return check_launch("gemm_tc_pack");
+}
+
+extern "C" int mrb_gemm_tc_pack_graphconv(const float* w0, const float* w1, int K, int D, void* image_fwd, void* image_bwd,
+                                          void* stream_) {
+    MRB_REQUIRE(w0 && w1 && image_fwd && image_bwd && K > 0 && D > 0, "gemm_tc_pack_graphconv: bad arguments");
+    MRB_REQUIRE((((uintptr_t)image_fwd | (uintptr_t)image_bwd) & 15) == 0, "gemm_tc_pack_graphconv: images must be 16-byte aligned");
+    // forward operand: B(k, n) = [W0 | W1](k, n), K x 2D;  input-gradient operand: B(k, n) = [W0 | W1](n, k), 2D x K
+    const Plan pf = make_plan(K, 2 * D), pb = make_plan(2 * D, K);
+    PackParams a, b;
+    a.src0 = w0; a.src1 = w1; a.sk = D; a.sn = 1; a.split_axis = 1; a.split_at = D;
+    a.K = K; a.N = 2 * D; a.NT = pf.NT; a.nchunks = pf.nchunks; a.ntiles = pf.ntiles; a.image = (unsigned char*)image_fwd;
+    b.src0 = w0; b.src1 = w1; b.sk = 1; b.sn = D; b.split_axis = 2; b.split_at = D;
+    b.K = 2 * D; b.N = K; b.NT = pb.NT; b.nchunks = pb.nchunks; b.ntiles = pb.ntiles; b.image = (unsigned char*)image_bwd;
+    const long long ta = (long long)pf.ntiles * pf.nchunks * pf.NT * BK, tb = (long long)pb.ntiles * pb.nchunks * pb.NT * BK;
+    k_pack_b2<<<(unsigned)ceil_div64(ta + tb, 256), 256, 0, (cudaStream_t)stream_>>>(a, b, ta);
+    return check_launch("gemm_tc_pack_graphconv");
 }
 
 extern "C" int mrb_gemm_tc(const float* A, int lda, int M, int K, const void* image, int N, float* C, int ldc,

@@ -291,8 +291,17 @@ class _GraphConv(torch.autograd.Function):
         D = w0.shape[1]
         y = torch.empty(n, 2 * D, dtype=torch.float32, device=x.device)
         yp = _lib.ptr(y)
+        ctx.img_bwd = None
         if _use_tc(K, 2 * D):      # one tensor-core pass over x for [x W0 | x W1]
-            img = tc_pack(w0, w1, D, 1, 1, D, K, 2 * D)
+            if ctx.needs_input_grad[0] and _use_tc(2 * D, K):
+                # the operand image of the input gradient is packed by the same launch (the weights cannot change between
+                # this forward and its backward: autograd would raise on an in-place update of a saved tensor)
+                lib = _lib.load()
+                img = torch.empty(lib.mrb_gemm_tc_image_bytes(K, 2 * D), dtype=torch.uint8, device=x.device)
+                ctx.img_bwd = torch.empty(lib.mrb_gemm_tc_image_bytes(2 * D, K), dtype=torch.uint8, device=x.device)
+                _lib.call("mrb_gemm_tc_pack_graphconv", _lib.ptr(w0), _lib.ptr(w1), K, D, _lib.ptr(img), _lib.ptr(ctx.img_bwd))
+            else:
+                img = tc_pack(w0, w1, D, 1, 1, D, K, 2 * D)
             tc_gemm(xp, ldx, n, K, img, 2 * D, yp, 2 * D)
         else:
             _gemm(False, False, n, D, K, xp, ldx, _lib.ptr(w0), D, 0.0, yp, 2 * D)
@@ -327,7 +336,7 @@ class _GraphConv(torch.autograd.Function):
             gx = _padded_rows(n, K, x.device)      # 16-byte aligned rows: coalesced epilogue of the tensor-core kernel
             ldgx, gxp = gx.stride(0), gx.data_ptr()
             if _use_tc(2 * D, K):  # gx = [gz | A^T gz] @ [W0 | W1]^T in one pass
-                img = tc_pack(w0, w1, 1, D, 2, D, 2 * D, K)
+                img = ctx.img_bwd if ctx.img_bwd is not None else tc_pack(w0, w1, 1, D, 2, D, 2 * D, K)
                 tc_gemm(gp, 2 * D, n, 2 * D, img, K, gxp, ldgx)
             else:
                 _gemm(False, True, n, K, D, gp, 2 * D, _lib.ptr(w0), D, 0.0, gxp, ldgx)
