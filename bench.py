@@ -93,6 +93,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------
 # workload
 # ---------------------------------------------------------------------------------------------------------------
+STARTUP_SECONDS = 2.0                   # untimed start-up phase of the CUDA arm (see run_cuda)
 KNN_DRAM_BYTES_PER_LAUNCH = 11.74e6      # ncu dram__bytes_read+write of one k_nn_grid<10> launch (profiles/)
 
 
@@ -178,6 +179,26 @@ def run_cuda(args):
     if sampler:
         sampler.start()
         time.sleep(0.5)
+    # ---- process start-up (untimed) ---------------------------------------------------------------------------
+    # Two one-off effects of a fresh process were measured to land exactly where a 20-step timed region sits:
+    #  * the ~11th step of EVERY loop bracketed by freshly created timing events stalled the launching thread for
+    #    20 - 130 ms (resident and e2e loops alike, never again in a 120-step run): the driver grows its pool of timing
+    #    events in chunks.  The pool is grown here once (2048 events recorded and released).
+    #  * the first ~12 steps ramp from 7.4 to 6.3 ms (clocks, allocator growth): the same step is run untimed for
+    #    STARTUP_SECONDS before the W warm-up steps.  Both are start-up cost, not steady-state throughput.
+    # (the driver grows its pool of timing events in chunks, which stalls the launching thread: grow it now)
+    _pool = [torch.cuda.Event(enable_timing=True) for _ in range(2048)]
+    for e in _pool:
+        e.record()
+    torch.cuda.synchronize()
+    del _pool
+    t_start = time.perf_counter()
+    startup_steps = 0
+    while time.perf_counter() - t_start < STARTUP_SECONDS:
+        step(vox_d, fmap_d)
+        startup_steps += 1
+        if startup_steps % 8 == 0:
+            torch.cuda.synchronize()
     # ---- warm-up -------------------------------------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
         losses = step(vox_d, fmap_d)
@@ -207,6 +228,8 @@ def run_cuda(args):
     # ---- timed region 2: end to end through the module API from pinned host memory --------------------------------
     ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     host_losses = None
+    for _ in range(2):      # untimed: first use of the H2D / D2H path (new allocation sizes, pinned-copy staging)
+        step(vox_pin.to(dev, non_blocking=True), fmap_pin.to(dev, non_blocking=True).requires_grad_())["chamfer_loss"].detach().cpu()
     sync_all()
     host_phase = []
     for a, b in ev2:
@@ -317,6 +340,8 @@ def run_cuda(args):
                                    % (B, GRID, THRESH, IMG),
                        "global_batch": B * world, "parallelism": "mesh-sharded dp%d, NCCL grad all-reduce(SUM)" % world,
                        "per_gpu": stats, "l2": "256 MiB flush write between timed iterations",
+                       "startup": "%d untimed steps (%.0f s) + timing-event pool pre-grown, before the W warm-up steps"
+                                  % (startup_steps, STARTUP_SECONDS),
                        "optimizer": "none (metric is fwd+bwd)"},
             "e2e": {"value": round(total_meshes / (e2e_ms * 1e-3), 2), "unit": "meshes/s",
                     "h2d_bytes_per_step": int(vox_pin.numel() * 4 + fmap_pin.numel() * 4), "d2h_bytes_per_step": 12,

@@ -24,8 +24,12 @@ torch.cuda.synchronize()
 import gc; gc.disable()
 R = "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 NSTEP = int(sys.argv[1]) if len(sys.argv) > 1 else 60
-for name, fields, ms in (("none", None, 0), ("clocks+reasons @200ms", "clocks.sm,clocks.max.sm," + R, 200), ("none again", None, 0),
-                         ("clocks only @200ms", "clocks.sm,clocks.max.sm", 200), ("clocks+reasons @50ms", "clocks.sm,clocks.max.sm," + R, 50)):
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+FLUSH = False
+for name, fields, ms in (("none", None, 0), ("flush only", "F", 0), ("flush + sampler @200ms", "F" + "clocks.sm,clocks.max.sm," + R, 200),
+                         ("none again", None, 0), ("flush only again", "F", 0)):
+    FLUSH = bool(fields) and fields.startswith("F")
+    fields = fields[1:] if FLUSH else fields
     proc = None
     if fields:
         proc = subprocess.Popen([shutil.which("nvidia-smi"), "-i", "0", "--query-gpu=" + fields, "--format=csv,noheader,nounits", "-lms", str(ms)],
@@ -33,6 +37,8 @@ for name, fields, ms in (("none", None, 0), ("clocks+reasons @200ms", "clocks.sm
         time.sleep(1.0)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(NSTEP)]
     for a, b in ev:
+        if FLUSH:
+            flush.zero_()
         a.record(); step(); b.record()
     torch.cuda.synchronize()
     t = sorted(a.elapsed_time(b) for a, b in ev)
