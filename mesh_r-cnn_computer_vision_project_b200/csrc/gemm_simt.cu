@@ -235,7 +235,7 @@ extern "C" int mrb_sgemm(int transA, int transB, int M, int N, int K, const floa
     }
     if (K > 0 && transA && !transB && M <= SKINNY && N <= 256) {
         k_scale_rows<<<(unsigned)ceil_div64((long long)M * N, 256), 256, 0, s>>>(C, M, N, ldc, beta);
-        const int rpb = max(256, ceil_div(K, kNumSMs));      // one block per SM: every block adds M * N atomics onto the same addresses
+        const int rpb = max(64, ceil_div(K, 4 * kNumSMs));
         if (M <= 4) k_skinny_tn<4><<<ceil_div(K, rpb), 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, rpb);
         else k_skinny_tn<SKINNY><<<ceil_div(K, rpb), 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, rpb);
         return check_launch("sgemm");
