@@ -147,3 +147,20 @@ def test_bench_reference_arm_extra_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                        capture_output=True, text=True, timeout=120, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_bench_time_based_loops_issue_no_collective():
+    """A loop bounded by wall-clock time runs a different number of iterations on every rank, so it must not contain the
+    step's NCCL all-reduce (bench.py's start-up phase once did: deadlock at N > 1)."""
+    import ast
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    tree = ast.parse(src)
+    checked = 0
+    for node in ast.walk(tree):
+        if isinstance(node, ast.While) and "perf_counter" in ast.get_source_segment(src, node.test):
+            for call in ast.walk(node):
+                if isinstance(call, ast.Call) and getattr(call.func, "id", None) == "step":
+                    kw = {k.arg: k.value for k in call.keywords}
+                    assert "exchange" in kw and isinstance(kw["exchange"], ast.Constant) and kw["exchange"].value is False
+                    checked += 1
+    assert checked >= 1
