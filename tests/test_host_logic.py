@@ -164,3 +164,19 @@ def test_bench_time_based_loops_issue_no_collective():
                     assert "exchange" in kw and isinstance(kw["exchange"], ast.Constant) and kw["exchange"].value is False
                     checked += 1
     assert checked >= 1
+
+
+def test_bench_reference_arm_line_keeps_the_contract():
+    """`bench.py --impl reference` (the oracle port on the host cores) prints ONE JSON line with the contract's keys."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "meshes/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["steps"] == 1 and d["warmup"] == 0 and d["n_gpus"] == 1 and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "meshes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
