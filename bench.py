@@ -351,7 +351,7 @@ def run_cuda(args):
             "losses": {k: float(v) for k, v in zip(("chamfer", "normal", "edge"), host_losses)},
         }
         if args.cpu_baseline:
-            result["cpu_baseline"] = cpu_reference(steps=1, warmup=0, meshes=2)
+            result["cpu_baseline"] = cpu_reference(steps=4, warmup=1, meshes=2)    # ~10 s of host work on the box (1 mesh/s on 16 cores)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
