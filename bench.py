@@ -350,7 +350,7 @@ def run_cuda(args):
             "breakdown_ms": breakdown,
             "losses": {k: float(v) for k, v in zip(("chamfer", "normal", "edge"), host_losses)},
         }
-        if args.cpu_baseline:
+        if args.cpu_baseline and world == 1:          # the CPU arm is timed at N = 1 only (the other ranks would just wait)
             result["cpu_baseline"] = cpu_reference(steps=4, warmup=1, meshes=2)    # ~10 s of host work on the box (1 mesh/s on 16 cores)
     if world > 1:
         dist.barrier()
