@@ -129,6 +129,30 @@ int mrb_vert_align_fwd(const float* fmap, int n_img, int C, int Hm, int Wm, cons
 int mrb_vert_align_bwd(const float* gout, int ld_g, int n_img, int C, int Hm, int Wm, const float* pos,
                        const int32_t* vert_mesh, const int32_t* mesh_info, int SV, float* gfmap, void* stream);
 
+/* bf16 feature-map mode (north star: "bf16 features rtol 2e-2"): fmap is n_img x C x Hm x Wm bf16 (NCHW); the output
+ * stays fp32.  workspace: n_img*C*Hm*Wm bf16 elements (channels-last copy; NULL or C % 8 != 0 selects the
+ * lane-per-channel path).  The backward is mrb_vert_align_bwd into an fp32 gradient map (the caller casts). */
+int mrb_vert_align_fwd_bf16(const void* fmap, int n_img, int C, int Hm, int Wm, const float* pos, const int32_t* vert_mesh,
+                            const int32_t* mesh_info, int SV, float* out, int ld_out, void* workspace, void* stream);
+
+/* VertexAlign fused with the bias-free linear layer that follows it in the ShapeNet stages (reference
+ * meshRCNN/layers.py:115,151-155 and :192,230):  linear(align(f))[v] = sum_m mask_{v,m} * T_m[img(v)*HW_m + texel_m(v)]
+ * with T_m = rows(f_m) @ W_m^T the per-texel projections (computed once per step with mrb_gemm_tc).
+ *   mrb_feature_map_to_rows   NCHW map (dtype 0 = fp32, 1 = bf16) -> channels-last fp32 rows (n_img*HW x C)
+ *   mrb_rows_to_feature_map   channels-last fp32 rows (pitch ld_rows) -> NCHW fp32 (gradient of a map)
+ *   mrb_vert_align_proj_fwd   T: packed texel projections, map m occupying rows [n_img * sum_{m'<m} HW_m', ...) in
+ *                             (image, x1, y1) order, D columns; map_size_host: n_maps (<= 8) map sizes Hm == Wm, a HOST
+ *                             array (read during the call);  out[v, 0:D] = sum_m mask * T[row_m(v)]
+ *   mrb_vert_align_proj_bwd   gT (same shape as T, overwritten): gT[row_m(v)] += mask * gout[v]  (fp32 reductions)
+ * D % 4 == 0; T, gT, out rows 16-byte aligned.  Vertex positions receive no gradient (layers.py:592). */
+int mrb_feature_map_to_rows(const void* fmap, int dtype, int n_img, int C, int HW, float* rows, void* stream);
+int mrb_rows_to_feature_map(const float* rows, int ld_rows, int n_img, int C, int HW, float* gfmap, void* stream);
+int mrb_vert_align_proj_fwd(const float* T, int D, int n_maps, const int* map_size_host, int n_img, const float* pos,
+                            const int32_t* vert_mesh, const int32_t* mesh_info, int SV, float* out, int ld_out, void* stream);
+int mrb_vert_align_proj_bwd(const float* gout, int ld_g, int D, int n_maps, const int* map_size_host, int n_img,
+                            const float* pos, const int32_t* vert_mesh, const int32_t* mesh_info, int SV, float* gT,
+                            void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Surface sampling -- replaces utils/mesh_sampling.py:6-57 (sample, surface_areas), utils/process.py:7-20
  * (normalize_mesh) and the per-mesh loop of batched_mesh_sampling (meshRCNN/loss_functions.py:80-89).

@@ -632,11 +632,8 @@ static void launch_nn(const float4* a, const float4* b, const float2* trange_b, 
 static bool pack_cloud(const float* pts, int B, int P, float4* out, float2* trange, cudaStream_t s) {
     if (P <= SORT_MAX) {
         const size_t smem = (size_t)NBUCKET * 4 + (size_t)P * 4;
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(k_sort_x, cudaFuncAttributeMaxDynamicSharedMemorySize, NBUCKET * 4 + SORT_MAX * 4);
-            attr_set = true;
-        }
+        static SmemOptIn optin;
+        ensure_dynamic_smem(k_sort_x, NBUCKET * 4 + SORT_MAX * 4, optin, "knn_fwd (x sort)");   // failure surfaces at the launch check
         k_sort_x<<<B, 1024, smem, s>>>(pts, P, out, trange, ceil_div(P, TILE));
         return true;
     }
@@ -702,11 +699,8 @@ extern "C" int mrb_knn_fwd_algo(const float* a, const float* b, int B, int P, in
     if (algo == 2 || (algo == 0 && grid_ok)) {
         const int Ga = grid_cells(P), Gb = grid_cells(Q);
         const int G = max(Ga, Gb);
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(k_grid_build, cudaFuncAttributeMaxDynamicSharedMemorySize, GMAX * GMAX * GMAX * 4);
-            attr_set = true;
-        }
+        static SmemOptIn optin;
+        if (int rc = ensure_dynamic_smem(k_grid_build, GMAX * GMAX * GMAX * 4, optin, "knn_fwd (cell grid)")) return rc;
         k_grid_build<<<2 * B, 1024, (size_t)G * G * G * 4, s>>>(a, b, B, P, Q, Ga, Gb, w.pa, w.pb, w.csa, w.csb, w.ha, w.hb,
                                                                 sqrtf(GRID_C0 * (float)max(k, 1)));
 #define MRB_NNG(KK)                                                                                                   \

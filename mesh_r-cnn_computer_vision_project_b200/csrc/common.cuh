@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 
 #define MRB_OK 0
 #define MRB_ERR_ARG 1
@@ -29,6 +30,33 @@ inline int check_launch(const char* what) {
             return MRB_ERR_ARG;           \
         }                                 \
     } while (0)
+
+// Opt-in to > 48 KB of dynamic shared memory.  cudaFuncSetAttribute applies to the *current device*, so the "already
+// done" state is one bit per device ordinal (a process may drive several GPUs from several threads, like the reference's
+// thread-per-GPU CustomDP, dataParallel/dataParallel.py:33).  The attribute call is idempotent, so two threads racing on
+// the same device both succeed; the bit is only a fast path.  Devices >= 64 set the attribute on every call.
+struct SmemOptIn {
+    std::atomic<unsigned long long> done{0};
+};
+template <typename KernelT>
+inline int ensure_dynamic_smem(KernelT kernel, int bytes, SmemOptIn& st, const char* what) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        set_error("%s: cudaGetDevice: %s", what, cudaGetErrorString(e));
+        return MRB_ERR_CUDA;
+    }
+    const unsigned long long bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0ull;
+    if (bit && (st.done.load(std::memory_order_acquire) & bit)) return MRB_OK;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) {
+        set_error("%s: cannot reserve %d bytes of dynamic shared memory on device %d: %s", what, bytes, dev,
+                  cudaGetErrorString(e));
+        return MRB_ERR_CUDA;
+    }
+    if (bit) st.done.fetch_or(bit, std::memory_order_release);
+    return MRB_OK;
+}
 
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
 

@@ -805,15 +805,8 @@ extern "C" int mrb_gemm_tc(const float* A, int lda, int M, int K, const void* im
                 lda, ldc);
     MRB_REQUIRE(((uintptr_t)image & 15) == 0, "gemm_tc: image must be 16-byte aligned");
     if (M == 0) return MRB_OK;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
-        if (e != cudaSuccess) {
-            set_error("gemm_tc: cannot reserve %d bytes of shared memory: %s", TC_SMEM_LIMIT, cudaGetErrorString(e));
-            return MRB_ERR_CUDA;
-        }
-        attr_set = true;
-    }
+    static SmemOptIn optin;
+    if (int rc = ensure_dynamic_smem(k_gemm_tc, TC_SMEM_LIMIT, optin, "gemm_tc")) return rc;
     const Plan pl = make_plan(K, N);
     // The tensor-core fp32 accumulate truncates, so the error of an accumulator grows with the number of MMAs chained
     // into it.  K is therefore processed in segments of SEG chunks (1024 columns); every segment is a full pass whose
@@ -851,16 +844,9 @@ extern "C" int mrb_gemm_tc_wgrad(const float* X, int ldx, const float* G, int ld
                 "gemm_tc_wgrad: C rows must be 16-byte aligned");
     MRB_REQUIRE(Kin > 0 && V >= 0 && ldx >= Kin && ldg >= N, "gemm_tc_wgrad: bad shape");
     if (V == 0) return MRB_OK;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_gemm_tn<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_gemm_tn<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e != cudaSuccess) {
-            set_error("gemm_tc_wgrad: cannot reserve shared memory: %s", cudaGetErrorString(e));
-            return MRB_ERR_CUDA;
-        }
-        attr_set = true;
-    }
+    static SmemOptIn optin8, optin4;
+    if (int rc = ensure_dynamic_smem(k_gemm_tn<8, 1>, SMEM_BYTES, optin8, "gemm_tc_wgrad")) return rc;
+    if (int rc = ensure_dynamic_smem(k_gemm_tn<4, 2>, SMEM_BYTES, optin4, "gemm_tc_wgrad")) return rc;
     const int tail = (Kin > BM && Kin % BM <= TN_TAIL_MAX) ? Kin % BM : 0;   // e.g. the 3 position columns of a stage input
     Kin -= tail;
     ParamsTN p;

@@ -17,43 +17,11 @@
 // full 128-byte lines, and 16-32 rows per warp are in flight.  Rows that are not 16-byte aligned (C % 4 != 0) fall back
 // to the lane-per-channel kernel below.
 #include "common.cuh"
+#include "valign.cuh"
 #include "../../include/meshrcnn_b200.h"
 
 namespace mrb {
 namespace valign {
-
-struct Texel {
-    int img;     // image index
-    int xy;      // x1 * Wm + y1
-    int valid;   // mask
-};
-
-// per-mesh record: image index, image height, image width
-__device__ __forceinline__ Texel project(const float* __restrict__ pos, const int32_t* __restrict__ vert_mesh,
-                                         const int32_t* __restrict__ mesh_info, int v, int Hm, int Wm) {
-    const int mesh = vert_mesh[v];
-    const int img = mesh_info[3 * mesh + 0];
-    const float H = (float)mesh_info[3 * mesh + 1], W = (float)mesh_info[3 * mesh + 2];
-    const float p0 = pos[3 * (size_t)v + 0], p1 = pos[3 * (size_t)v + 1], p2 = pos[3 * (size_t)v + 2];
-    // layers.py:557-558 (separate fp32 ops: div, mul, add)
-    float h = __fadd_rn(__fmul_rn(248.f, __fdiv_rn(p1, p2)), 111.5f);
-    float w = __fadd_rn(__fmul_rn(248.f, __fdiv_rn(p0, -p2)), 111.5f);
-    // :561-562  clamp(min=0, max=H-1)
-    h = fminf(fmaxf(h, 0.f), H - 1.f);
-    w = fminf(fmaxf(w, 0.f), W - 1.f);
-    // :577-578  divisor is a python double cast to fp32; true division
-    const float sx = (float)((double)mesh_info[3 * mesh + 2] / (double)Wm);
-    const float sy = (float)((double)mesh_info[3 * mesh + 1] / (double)Hm);
-    const float x = __fdiv_rn(w, sx), y = __fdiv_rn(h, sy);
-    const int x1 = (int)floorf(x), y1 = (int)floorf(y);
-    const int x2 = min((int)ceilf(x), Wm - 1), y2 = min((int)ceilf(y), Hm - 1);   // :583-584
-    Texel t;
-    t.img = img;
-    // x (from w, scaled by size_x = last dim) indexes the H axis; y indexes the W axis (:587)
-    t.xy = x1 * Wm + y1;
-    t.valid = (x2 > x1) && (y2 > y1) && x1 >= 0 && y1 >= 0 && x1 < Hm && y1 < Wm;
-    return t;
-}
 
 __global__ void __launch_bounds__(256) k_fwd(const float* __restrict__ fmap, int C, int Hm, int Wm,
                                              const float* __restrict__ pos, const int32_t* __restrict__ vert_mesh,
@@ -193,11 +161,8 @@ extern "C" int mrb_vert_align_fwd(const float* fmap, int n_img, int C, int Hm, i
     const int row_bytes = C * 4;
     const int slots = min(32, VA_WARP_BYTES / row_bytes);
     const size_t smem = ((row_bytes + 127) & ~127) + (size_t)VA_WARPS * VA_WARP_BYTES;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_fwd_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 + VA_WARPS * VA_WARP_BYTES);
-        attr_set = true;
-    }
+    static SmemOptIn optin;
+    if (int rc = ensure_dynamic_smem(k_fwd_bulk, 16384 + VA_WARPS * VA_WARP_BYTES, optin, "vert_align_fwd")) return rc;
     const int batches = ceil_div(SV, slots);
     const int grid = min(ceil_div(batches, VA_WARPS), 2 * kNumSMs);
     k_fwd_bulk<<<grid, VA_WARPS * 32, smem, s>>>(workspace, C, Hm, Wm, pos, vert_mesh, mesh_info, SV, out, ld_out, slots);

@@ -4,6 +4,7 @@ Nothing here computes on the CPU and nothing falls back to PyTorch ops for the h
 allocates its outputs with torch (device memory only) and launches hand-written sm_100a kernels on the
 caller's current stream through ``_lib.call``.
 """
+import ctypes
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -20,8 +21,15 @@ CUBIFY_CORNERS = (
 
 
 def _require_cuda(t: Tensor, what: str) -> None:
+    """The kernels are launched on the *current* device's current stream (``_lib.stream_ptr``), so a tensor that lives on
+    another GPU is rejected instead of being handed to a kernel running on the wrong device: multi-GPU callers (one
+    thread per GPU like the reference's ``parallel_apply``, dataParallel/dataParallel.py:33) run each replica under
+    ``torch.cuda.device(i)``."""
     if not isinstance(t, Tensor) or not t.is_cuda:
         raise RuntimeError("meshrcnn_b200.%s: expected a CUDA tensor -- the hot path has no CPU fallback" % what)
+    if t.device.index != torch._C._cuda_getDevice():
+        raise RuntimeError("meshrcnn_b200.%s: tensor lives on %s but the current CUDA device is cuda:%d -- call under "
+                           "`with torch.cuda.device(tensor.device):`" % (what, t.device, torch._C._cuda_getDevice()))
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -363,6 +371,13 @@ def graph_conv(x: Tensor, adj: Tensor, w0: Tensor, w1: Tensor) -> Tensor:
 # ----------------------------------------------------------------------------------------------------------
 # VertexAlign
 # ----------------------------------------------------------------------------------------------------------
+def _map_tensor(f: Tensor) -> Tensor:
+    """Feature maps are consumed as fp32 or bf16 NCHW (north star: "bf16 features rtol 2e-2"); anything else -> fp32."""
+    if f.dtype == torch.bfloat16:
+        return f if f.is_contiguous() else f.contiguous()
+    return _f32c(f)
+
+
 class _VertAlign(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pos, vert_mesh, mesh_info, *fmaps):
@@ -373,16 +388,17 @@ class _VertAlign(torch.autograd.Function):
             _require_cuda(f, "VertexAlign")
             if f.dim() != 4:
                 raise RuntimeError("VertexAlign: feature maps must be N x C x H x W")
-            maps.append(_f32c(f))
+            maps.append(_map_tensor(f))
         SV = pos_c.shape[0]
         ctot = sum(m.shape[1] for m in maps)
         out = torch.empty(SV, ctot, dtype=torch.float32, device=pos.device)
         off = 0
         for m in maps:
             n_img, C, Hm, Wm = m.shape
-            ws = torch.empty_like(m)          # channels-last copy for the TMA gather
-            _lib.call("mrb_vert_align_fwd", _lib.ptr(m), n_img, C, Hm, Wm, _lib.ptr(pos_c), _lib.ptr(vert_mesh),
-                      _lib.ptr(mesh_info), SV, _lib.ptr(out) + 4 * off, ctot, _lib.ptr(ws))
+            ws = torch.empty_like(m)          # channels-last copy for the row gather
+            name = "mrb_vert_align_fwd_bf16" if m.dtype == torch.bfloat16 else "mrb_vert_align_fwd"
+            _lib.call(name, _lib.ptr(m), n_img, C, Hm, Wm, _lib.ptr(pos_c), _lib.ptr(vert_mesh), _lib.ptr(mesh_info), SV,
+                      _lib.ptr(out) + 4 * off, ctot, _lib.ptr(ws))
             off += C
         ctx.save_for_backward(pos_c, vert_mesh, mesh_info)
         ctx.shapes = [tuple(m.shape) for m in maps]
@@ -421,6 +437,120 @@ def vert_align(img_features: Sequence[Tensor], vertex_positions: Tensor, vertice
     vert_mesh = vertex_mesh_ids(vertices_per_mesh, vertex_positions.shape[0], dev, topo)
     info = mesh_info_table(mesh_index, image_sizes, dev)
     return _VertAlign.apply(vertex_positions, vert_mesh, info, *img_features)
+
+
+class _VertAlignLinear(torch.autograd.Function):
+    """linear(VertexAlign(maps))  =  sum over maps of  mask * (texel rows @ W_m^T)[texel(v)]   (csrc/align_proj.cu).
+
+    The texels of every map are projected once on the tensor cores (n_img * HW_m rows instead of SV), every vertex then
+    gathers and sums one D-wide row per map; the SV x sum(C_m) VertexAlign output is never formed.  Replaces
+    ``self.linear(self.vertAlign(...))`` of the ShapeNet stages (reference meshRCNN/layers.py:151-155,226-230)."""
+
+    @staticmethod
+    def forward(ctx, pos, vert_mesh, mesh_info, weight, *fmaps):
+        _require_cuda(pos, "VertexAlign+linear")
+        lib = _lib.load()
+        dev = pos.device
+        pos_c = _f32c(pos.detach())
+        w = _f32c(weight)
+        D, ctot = w.shape
+        maps = []
+        for f in fmaps:
+            _require_cuda(f, "VertexAlign+linear")
+            if f.dim() != 4 or f.shape[2] != f.shape[3]:
+                raise RuntimeError("VertexAlign: feature maps must be N x C x H x W with H == W (the reference indexes H "
+                                   "with the x coordinate)")
+            maps.append(_map_tensor(f))
+        n_img = maps[0].shape[0]
+        if any(m.shape[0] != n_img for m in maps) or sum(m.shape[1] for m in maps) != ctot:
+            raise RuntimeError("VertexAlign+linear: maps %s do not match the %d x %d weight" %
+                               ([tuple(m.shape) for m in maps], D, ctot))
+        if D % 4 or not 1 <= len(maps) <= 8:
+            raise RuntimeError("VertexAlign+linear: out_features %% 4 == 0 and 1..8 maps required")
+        sizes = (ctypes.c_int * len(maps))(*[int(m.shape[2]) for m in maps])
+        rows_per_map = [n_img * m.shape[2] * m.shape[3] for m in maps]
+        T = torch.empty(sum(rows_per_map), D, dtype=torch.float32, device=dev)
+        rows_cl, r0, c0 = [], 0, 0
+        for m, R in zip(maps, rows_per_map):
+            C = m.shape[1]
+            cl = torch.empty(R, C, dtype=torch.float32, device=dev)
+            _lib.call("mrb_feature_map_to_rows", _lib.ptr(m), int(m.dtype == torch.bfloat16), n_img, C, R // n_img, _lib.ptr(cl))
+            # T[r0:r0+R] = cl @ W[:, c0:c0+C]^T : logical operand B(k, n) = W[n, c0 + k]
+            if _use_tc(C, D):
+                img = torch.empty(lib.mrb_gemm_tc_image_bytes(C, D), dtype=torch.uint8, device=dev)
+                _lib.call("mrb_gemm_tc_pack", w.data_ptr() + 4 * c0, None, 1, ctot, 0, 0, C, D, _lib.ptr(img))
+                tc_gemm(_lib.ptr(cl), C, R, C, img, D, T.data_ptr() + 4 * r0 * D, D)
+            else:
+                _gemm(False, True, R, D, C, _lib.ptr(cl), C, w.data_ptr() + 4 * c0, ctot, 0.0, T.data_ptr() + 4 * r0 * D, D)
+            rows_cl.append(cl)
+            r0 += R
+            c0 += C
+        SV = pos_c.shape[0]
+        out = torch.empty(SV, D, dtype=torch.float32, device=dev)
+        _lib.call("mrb_vert_align_proj_fwd", _lib.ptr(T), D, len(maps), sizes, n_img, _lib.ptr(pos_c), _lib.ptr(vert_mesh),
+                  _lib.ptr(mesh_info), SV, _lib.ptr(out), D)
+        ctx.save_for_backward(pos_c, vert_mesh, mesh_info, w, *rows_cl)
+        ctx.meta = (sizes, n_img, [tuple(m.shape) for m in maps], [f.dtype for f in fmaps], rows_per_map)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        pos_c, vert_mesh, mesh_info, w = ctx.saved_tensors[:4]
+        rows_cl = ctx.saved_tensors[4:]
+        sizes, n_img, shapes, dtypes, rows_per_map = ctx.meta
+        lib = _lib.load()
+        dev = gout.device
+        D, ctot = w.shape
+        gout = _rows(gout)
+        SV = gout.shape[0]
+        gT = torch.empty(sum(rows_per_map), D, dtype=torch.float32, device=dev)
+        _lib.call("mrb_vert_align_proj_bwd", gout.data_ptr(), gout.stride(0), D, len(shapes), sizes, n_img, _lib.ptr(pos_c),
+                  _lib.ptr(vert_mesh), _lib.ptr(mesh_info), SV, _lib.ptr(gT))
+        gw = None
+        gwt = torch.zeros(ctot, D, dtype=torch.float32, device=dev) if ctx.needs_input_grad[3] else None
+        gmaps = []
+        r0 = c0 = 0
+        for i, (shape, R, cl) in enumerate(zip(shapes, rows_per_map, rows_cl)):
+            C = shape[1]
+            gt_ptr = gT.data_ptr() + 4 * r0 * D
+            if gwt is not None:             # dW_m^T (C x D) = rows_m^T @ gT_m
+                if _use_tc_wgrad(R, D):
+                    _lib.call("mrb_gemm_tc_wgrad", _lib.ptr(cl), C, gt_ptr, D, R, C, D, gwt.data_ptr() + 4 * c0 * D, None, D, D)
+                else:
+                    _gemm(True, False, C, D, R, _lib.ptr(cl), C, gt_ptr, D, 0.0, gwt.data_ptr() + 4 * c0 * D, D)
+            if ctx.needs_input_grad[4 + i]:  # d rows_m (R x C) = gT_m @ W[:, c0:c0+C] : B(k, n) = W[k, c0 + n]
+                g_rows = torch.empty(R, C, dtype=torch.float32, device=dev)
+                if _use_tc(D, C):
+                    img = torch.empty(lib.mrb_gemm_tc_image_bytes(D, C), dtype=torch.uint8, device=dev)
+                    _lib.call("mrb_gemm_tc_pack", w.data_ptr() + 4 * c0, None, ctot, 1, 0, 0, D, C, _lib.ptr(img))
+                    tc_gemm(gt_ptr, D, R, D, img, C, _lib.ptr(g_rows), C)
+                else:
+                    _gemm(False, False, R, C, D, gt_ptr, D, w.data_ptr() + 4 * c0, ctot, 0.0, _lib.ptr(g_rows), C)
+                g = torch.empty(shape, dtype=torch.float32, device=dev)
+                _lib.call("mrb_rows_to_feature_map", _lib.ptr(g_rows), C, n_img, C, R // n_img, _lib.ptr(g))
+                gmaps.append(g if dtypes[i] == torch.float32 else g.to(dtypes[i]))
+            else:
+                gmaps.append(None)
+            r0 += R
+            c0 += C
+        if gwt is not None:
+            gw = gwt.t().contiguous()       # nn.Linear stores out x in
+        return (None, None, None, gw) + tuple(gmaps)
+
+
+def vert_align_linear(img_features: Sequence[Tensor], vertex_positions: Tensor, vertices_per_mesh: Sequence[int],
+                      image_sizes, mesh_index: Sequence[int], weight: Tensor, topo: Optional[MeshTopology] = None) -> Tensor:
+    """``F.linear(VertexAlign()(img_features, ...), weight)`` (weight: out x sum(C_m), no bias) without forming the
+    SV x sum(C_m) matrix -- see ``_VertAlignLinear``."""
+    dev = vertex_positions.device
+    _require_cuda(vertex_positions, "VertexAlign")
+    if sum(int(m) for m in mesh_index) != len(vertices_per_mesh):
+        raise RuntimeError("VertexAlign: sum(mesh_index) must equal the number of meshes")
+    if sum(vertices_per_mesh) != vertex_positions.shape[0]:
+        raise RuntimeError("VertexAlign: vertices_per_mesh does not sum to the number of vertex positions")
+    vert_mesh = vertex_mesh_ids(vertices_per_mesh, vertex_positions.shape[0], dev, topo)
+    info = mesh_info_table(mesh_index, image_sizes, dev)
+    return _VertAlignLinear.apply(vertex_positions, vert_mesh, info, weight, *img_features)
 
 
 # ----------------------------------------------------------------------------------------------------------

@@ -119,6 +119,24 @@ def _default_mesh_index(mesh_index, image_sizes):
     return [1 for _ in image_sizes] if mesh_index is None else mesh_index
 
 
+# ShapeNet stages: evaluate linear(VertexAlign(maps)) as per-texel projections + a 128-wide row gather
+# (functional.vert_align_linear, csrc/align_proj.cu) instead of materialising the SV x 3840 VertexAlign output.
+# Same values up to fp32 summation order; False restores the literal two-step evaluation (used by the parity tests).
+FUSE_ALIGN_BOTTLENECK = True
+
+
+def _align_and_project(align: "VertexAlign", linear: nn.Linear, img_feature_maps, vertex_positions, vertice_index,
+                       image_sizes, mesh_index) -> Tensor:
+    """``linear(align(maps, positions, ...))`` of reference meshRCNN/layers.py:151-155 / :226-230."""
+    if not FUSE_ALIGN_BOTTLENECK or linear.bias is not None:
+        return linear(align(img_feature_maps, vertex_positions, vertice_index, image_sizes, mesh_index))
+    if align.training:                                          # the checks of VertexAlign.forward (layers.py:528-532)
+        assert len(vertice_index) == len(image_sizes)
+        assert list(mesh_index) == [1 for _ in image_sizes]
+    assert len(mesh_index) == len(image_sizes)
+    return F_.vert_align_linear(img_feature_maps, vertex_positions, vertice_index, image_sizes, mesh_index, linear.weight)
+
+
 def _stage_input(vertex_positions, pooled, vertex_features, use_input_features):
     parts = [vertex_positions, pooled]
     if vertex_features is not None:
@@ -150,8 +168,8 @@ class ResVertixRefineShapenet(nn.Module):
                 vertex_positions: Tensor, image_sizes: List, vertex_features: Optional[Tensor] = None,
                 mesh_index: List[int] = None) -> Tuple[Tensor, Tensor]:
         mesh_index = _default_mesh_index(mesh_index, image_sizes)
-        aligned = self.vertAlign(img_feature_maps, vertex_positions, vertice_index, image_sizes, mesh_index)
-        projected = self.linear(aligned)
+        projected = _align_and_project(self.vertAlign, self.linear, img_feature_maps, vertex_positions, vertice_index,
+                                       image_sizes, mesh_index)
         x = _stage_input(vertex_positions, projected, vertex_features, self.use_input_features)
         x = self.resGraphConv0(x, vertex_adjacency)
         x = self.resGraphConv1(x, vertex_adjacency)
@@ -180,8 +198,8 @@ class VertixRefineShapeNet(nn.Module):
                 vertex_positions: Tensor, image_sizes: List, mesh_index: List[int] = None,
                 vertex_features: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
         mesh_index = _default_mesh_index(mesh_index, image_sizes)
-        aligned = self.vertAlign(img_feature_maps, vertex_positions, vertice_index, image_sizes, mesh_index)
-        projected = self.linear0(aligned)
+        projected = _align_and_project(self.vertAlign, self.linear0, img_feature_maps, vertex_positions, vertice_index,
+                                       image_sizes, mesh_index)
         x = _stage_input(vertex_positions, projected, vertex_features, self.use_input_features)
         x = self.graphConv0(x, vertex_adjacency)
         x = self.graphConv1(F_.concat_cols([vertex_positions, x]), vertex_adjacency)

@@ -65,6 +65,109 @@ def test_vert_align_mesh_index_and_errors(lib):
         VertexAlign().eval()([f.cuda() for f in fm], pos.cuda(), [20, 30], sizes, mi)
 
 
+def _shapenet_align_case(B=3, n=700, seed=7, scale=0.25):
+    from meshrcnn_b200 import synthetic
+    shapes = [(c // 8, h, w) for (c, h, w) in synthetic.SHAPENET_MAPS]      # 32 + 64 + 128 + 256 = 480 channels
+    fms = [f * scale for f in synthetic.feature_maps(B, shapes, seed)]
+    pos = synthetic.in_frustum_positions(n, 137, seed + 1)
+    vpm = [n // B] * (B - 1) + [n - (B - 1) * (n // B)]
+    g = torch.Generator().manual_seed(seed + 2)
+    w = (torch.rand(128, 480, generator=g) - 0.5) * 0.2
+    go = torch.randn(n, 128, generator=g)
+    return fms, pos, vpm, [(137, 137)] * B, [1] * B, w, go
+
+
+def test_vert_align_linear_fused_vs_oracle_and_unfused(lib):
+    """linear(VertexAlign(maps)) evaluated as per-texel projections + a row gather (csrc/align_proj.cu) against the fp64
+    oracle (VertexAlign then the dense bottleneck, reference layers.py:151-155) and against the literal two-step CUDA path:
+    values and the gradients of the weight and of every map at rtol 1e-4."""
+    from meshrcnn_b200 import functional as F_
+    from meshrcnn_b200.layers import VertexAlign
+    fms, pos, vpm, sizes, mi, w, go = _shapenet_align_case()
+
+    def oracle(dt):
+        f = [x.to(dt).requires_grad_() for x in fms]
+        wd = w.to(dt).requires_grad_()
+        out = mesh_ops.vert_align(f, pos.to(dt), vpm, sizes, mi) @ wd.t()
+        (out * go.to(dt)).sum().backward()
+        return out.detach(), wd.grad, [x.grad for x in f]
+
+    want, want_gw, want_gf = oracle(torch.float64)
+    assert float((mesh_ops.vert_align(fms, pos, vpm, sizes, mi) != 0).float().mean()) > 0.5    # the gather is exercised
+
+    f_c = [x.cuda().requires_grad_() for x in fms]
+    w_c = w.cuda().requires_grad_()
+    out = F_.vert_align_linear(f_c, pos.cuda(), vpm, sizes, mi, w_c)
+    (out * go.cuda()).sum().backward()
+    close(out, want, what="fused out")
+    close(w_c.grad, want_gw, what="fused gW")
+    for i in range(4):
+        close(f_c[i].grad, want_gf[i], what="fused gmap%d" % i)
+
+    f_u = [x.cuda().requires_grad_() for x in fms]
+    w_u = w.cuda().requires_grad_()
+    out_u = F_.linear(VertexAlign().eval()(f_u, pos.cuda(), vpm, sizes, mi), w_u)
+    (out_u * go.cuda()).sum().backward()
+    close(out, out_u.detach().cpu(), what="fused vs unfused out")
+    close(w_c.grad, w_u.grad.cpu(), what="fused vs unfused gW")
+
+
+def test_vert_align_linear_all_masked_and_single_map(lib):
+    """Pipeline coordinates (half-integer voxel units) all clamp to the image border (SURVEY finding 8): the fused path
+    must return exact zeros and zero gradients there; plus the single-map / tiny-row-count (CUDA-core GEMM) branch."""
+    from meshrcnn_b200 import functional as F_, synthetic
+    fms, _, vpm, sizes, mi, w, go = _shapenet_align_case()
+    g = torch.Generator().manual_seed(11)
+    n = sum(vpm)                                                  # |p0/p2|, |p1/p2| >= 5: every projection clamps
+    pos = torch.stack([10 + 10 * torch.rand(n, generator=g), 10 + 10 * torch.rand(n, generator=g),
+                       -(1 + torch.rand(n, generator=g))], 1)
+    assert float(mesh_ops.vert_align(fms, pos, vpm, sizes, mi).abs().max()) == 0.0
+    f_c = [x.cuda().requires_grad_() for x in fms]
+    w_c = w.cuda().requires_grad_()
+    out = F_.vert_align_linear(f_c, pos.cuda(), vpm, sizes, mi, w_c)
+    assert float(out.abs().max()) == 0.0
+    (out * go.cuda()).sum().backward()
+    assert float(w_c.grad.abs().max()) == 0.0 and all(float(f.grad.abs().max()) == 0.0 for f in f_c)
+
+    fm = synthetic.feature_maps(2, [(12, 6, 6)], 3)              # K = 12 < 16: CUDA-core fallback GEMMs
+    p = synthetic.in_frustum_positions(50, 224, 4)
+    g = torch.Generator().manual_seed(5)
+    w1 = torch.randn(8, 12, generator=g)
+    want = mesh_ops.vert_align([fm[0].double()], p.double(), [20, 30], [(224, 224)] * 2, [1, 1]) @ w1.double().t()
+    got = F_.vert_align_linear([fm[0].cuda()], p.cuda(), [20, 30], [(224, 224)] * 2, [1, 1], w1.cuda())
+    close(got, want, what="single map")
+
+
+def test_vert_align_bf16_feature_maps(lib):
+    """bf16 feature-map mode (north star: bf16 features rtol 2e-2): the gather of a bf16 map equals the fp32 gather of
+    the same (rounded) values exactly, and stays within rtol 2e-2 of the fp64 oracle on the unrounded maps; the fused
+    bottleneck path accepts bf16 maps as well.  Gradients come back in bf16."""
+    from meshrcnn_b200 import functional as F_
+    from meshrcnn_b200.layers import VertexAlign
+    fms, pos, vpm, sizes, mi, w, go = _shapenet_align_case()
+    want = mesh_ops.vert_align([f.double() for f in fms], pos.double(), vpm, sizes, mi)
+    bf = [f.to(torch.bfloat16).cuda().requires_grad_() for f in fms]
+    out = VertexAlign().eval()(bf, pos.cuda(), vpm, sizes, mi)
+    assert out.dtype == torch.float32
+    same = VertexAlign().eval()([b.detach().float() for b in bf], pos.cuda(), vpm, sizes, mi)
+    assert torch.equal(out, same)
+    close(out, want, rtol=2e-2, what="bf16 gather")
+    gsel = torch.randn(out.shape, generator=torch.Generator().manual_seed(3))
+    (out * gsel.cuda()).sum().backward()
+    assert all(b.grad is not None and b.grad.dtype == torch.bfloat16 for b in bf)
+    f64 = [f.double().requires_grad_() for f in fms]
+    (mesh_ops.vert_align(f64, pos.double(), vpm, sizes, mi) * gsel.double()).sum().backward()
+    for i in range(4):
+        close(bf[i].grad.float(), f64[i].grad, rtol=2e-2, what="bf16 gmap%d" % i)
+    # odd channel count -> lane-per-channel kernel
+    odd = fms[0][:, :13].contiguous()
+    got = VertexAlign().eval()([odd.to(torch.bfloat16).cuda()], pos.cuda(), vpm, sizes, mi)
+    close(got, mesh_ops.vert_align([odd.double()], pos.double(), vpm, sizes, mi), rtol=2e-2, what="bf16 odd C")
+    # fused bottleneck with bf16 maps
+    fused = F_.vert_align_linear([b.detach() for b in bf], pos.cuda(), vpm, sizes, mi, w.cuda())
+    close(fused, want @ w.double().t(), rtol=2e-2, what="bf16 fused")
+
+
 # ---------------------------------------------------------------------------------------------------------------
 def test_aggregate_known_answer(lib):
     """reference tests/test_layers.py:16-26 (non-symmetric, unsorted-by-row-safe COO)."""
