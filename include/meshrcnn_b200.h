@@ -29,6 +29,10 @@ extern "C" {
 int mrb_version(void);
 const char* mrb_last_error(void);
 int mrb_device_info(int* sm_major, int* sm_minor, int* num_sms);
+/* FP32 FMA issue-rate microbenchmark (the measured peak of the FP32-issue-bound k-NN kernels): launches
+ * `blocks` CTAs of 256 threads running `iters` x 128 dependent-chain FMAs each and returns the flop count of the launch
+ * (2 per FMA), or -1 on error; the caller times it with CUDA events.  out: 1 float of device scratch. */
+long long mrb_fma_peak(float* out, int iters, int blocks, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Cubify  -- replaces Cubify.forward, reference meshRCNN/layers.py:403-484.

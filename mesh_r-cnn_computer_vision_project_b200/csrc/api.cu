@@ -37,3 +37,37 @@ extern "C" int mrb_device_info(int* sm_major, int* sm_minor, int* num_sms) {
     if (num_sms) *num_sms = p.multiProcessorCount;
     return MRB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// FP32 FMA issue-rate microbenchmark: the measured peak the FP32-issue-bound kernels (k-NN) are compared with
+// (MEASURED_PEAKS.json holds only HBM and bf16 figures).
+// ---------------------------------------------------------------------------------------------------------
+namespace mrb {
+constexpr int FMA_CHAINS = 16;     // independent dependency chains per thread (latency 4 x 4 issue slots are covered)
+constexpr int FMA_UNROLL = 8;
+__global__ void __launch_bounds__(256) k_fma_peak(float* __restrict__ out, int iters, float b, float c) {
+    float a[FMA_CHAINS];
+#pragma unroll
+    for (int i = 0; i < FMA_CHAINS; ++i) a[i] = (float)(threadIdx.x + i) * 1e-3f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < FMA_UNROLL; ++u)
+#pragma unroll
+            for (int i = 0; i < FMA_CHAINS; ++i) a[i] = fmaf(a[i], b, c);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < FMA_CHAINS; ++i) s += a[i];
+    if (s == 123.456f) out[0] = s;     // keeps the chains alive; practically never true
+}
+}  // namespace mrb
+
+extern "C" long long mrb_fma_peak(float* out, int iters, int blocks, void* stream_) {
+    if (!out || iters <= 0 || blocks <= 0) {
+        mrb::set_error("fma_peak: bad arguments");
+        return -1;
+    }
+    mrb::k_fma_peak<<<blocks, 256, 0, (cudaStream_t)stream_>>>(out, iters, 0.999f, 1e-3f);
+    if (mrb::check_launch("fma_peak")) return -1;
+    return 2LL * blocks * 256 * (long long)iters * mrb::FMA_CHAINS * mrb::FMA_UNROLL;     // flop issued by this launch
+}

@@ -25,12 +25,21 @@ def split_to_n(n_items: int, n_parts: int) -> List[Tuple[int, int]]:
     return out
 
 
-def balanced_split(costs: List[float], n_parts: int) -> List[List[int]]:
-    """Greedy longest-processing-time assignment of meshes to ranks by a per-mesh cost (e.g. occupied-voxel count);
-    optional throughput mode (mesh sizes vary ~1.4x), not used for parity runs."""
-    order = sorted(range(len(costs)), key=lambda i: -costs[i])
-    loads = [0.0] * n_parts
+def balanced_split(costs: List[float], n_parts: int, equal_counts: bool = False) -> List[List[int]]:
+    """Assignment of meshes to ranks by a per-mesh cost (e.g. the occupied-voxel count; mesh sizes vary ~1.4x) -- the
+    throughput mode of SURVEY.md 8(e), not used for parity runs (those keep ``split_to_n``).
+
+    ``equal_counts=False``: greedy longest-processing-time (each mesh to the least loaded rank).
+    ``equal_counts=True``: meshes sorted by cost are dealt in snake order (0..n-1, n-1..0, ...), so every rank gets the
+    same number of meshes (+-1) -- the per-mesh constant work (10k-point sampling, k-NN) stays balanced as well."""
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
     parts: List[List[int]] = [[] for _ in range(n_parts)]
+    if equal_counts:
+        for pos, i in enumerate(order):
+            rnd, k = divmod(pos, n_parts)
+            parts[k if rnd % 2 == 0 else n_parts - 1 - k].append(i)
+        return [sorted(p) for p in parts]
+    loads = [0.0] * n_parts
     for i in order:
         r = min(range(n_parts), key=lambda j: loads[j])
         parts[r].append(i)
@@ -38,32 +47,144 @@ def balanced_split(costs: List[float], n_parts: int) -> List[List[int]]:
     return [sorted(p) for p in parts]
 
 
+def _dist_on() -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
 class FlatGradBucket:
     """All parameter gradients live in one contiguous fp32 buffer (``p.grad`` are views into it), so the step's
-    exchange is a single all-reduce launch: 1.9 MB for the Pix3D head, 8.9 MB for the residual ShapeNet head."""
+    exchange is a single all-reduce launch: 1.9 MB for the Pix3D head, 8.9 MB for the residual ShapeNet head.
+
+    ``optimizer.zero_grad()`` / ``module.zero_grad()`` default to ``set_to_none=True`` (torch >= 2.0), which drops the
+    views: the next backward then allocates fresh ``.grad`` tensors and an all-reduce of the flat buffer would silently
+    exchange stale zeros.  ``zero()`` therefore re-binds the views and ``all_reduce()`` first calls ``sync_views()``,
+    which copies any detached ``.grad`` back into the buffer and re-attaches it -- use ``bucket.zero()`` instead of
+    ``zero_grad()``, but a training loop that calls ``zero_grad(set_to_none=True)`` still reduces the right values."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter]):
         self.params = [p for p in params if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.offsets = []
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self.offsets.append(off)
             off += p.numel()
+        self._bind()
+
+    def _view(self, i: int) -> Tensor:
+        p = self.params[i]
+        return self.flat[self.offsets[i]:self.offsets[i] + p.numel()].view_as(p)
+
+    def _bind(self) -> None:
+        for i, p in enumerate(self.params):
+            p.grad = self._view(i)
+
+    def sync_views(self) -> int:
+        """Makes every ``p.grad`` a view of the flat buffer again (copying detached gradients into it; a parameter whose
+        ``.grad`` is None contributes zeros).  Returns the number of parameters that had to be re-attached."""
+        esz = self.flat.element_size()
+        base = self.flat.data_ptr()
+        fixed = 0
+        for i, p in enumerate(self.params):
+            g = p.grad
+            if g is not None and g.data_ptr() == base + esz * self.offsets[i] and g.is_contiguous():
+                continue
+            v = self._view(i)
+            if g is None:
+                v.zero_()
+            else:
+                v.copy_(g)
+            p.grad = v
+            fixed += 1
+        return fixed
 
     def zero(self) -> None:
         self.flat.zero_()
+        for i, p in enumerate(self.params):
+            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + self.flat.element_size() * self.offsets[i]:
+                p.grad = self._view(i)
 
     def all_reduce(self, async_op: bool = False):
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        self.sync_views()
+        if _dist_on():
             return dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
         return None
 
 
+class StagedGradBuckets:
+    """Overlapped gradient exchange ("launched as soon as the last stage's backward finishes its weight
+    grads and overlapped with the remaining backward"): one flat bucket per group of parameters (here: per refinement
+    stage).  A post-accumulate-grad hook counts the parameters of a group whose gradient of this backward pass is final;
+    when the last one arrives the group's all-reduce(SUM) is issued asynchronously -- backward runs the stages in reverse,
+    so stage 2's exchange overlaps the backward of stages 1 and 0.  ``finish()`` waits for the outstanding handles (and
+    issues the exchange of any group that did not complete, e.g. parameters without a gradient this step).
+
+    Like ``FlatGradBucket``, gradients are views into the group's flat buffer and the reduction is SUM (reference
+    ``reduce_add``, dataParallel/gather.py:13-28)."""
+
+    def __init__(self, groups: Iterable[Iterable[torch.nn.Parameter]]):
+        self.buckets = [FlatGradBucket(g) for g in groups]
+        self.enabled = True
+        self._pending = [0] * len(self.buckets)
+        self._issued = [False] * len(self.buckets)
+        self._handles = []
+        self._hooks = []
+        for gi, b in enumerate(self.buckets):
+            for p in b.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(gi)))
+        self.zero()
+
+    @classmethod
+    def per_stage(cls, head) -> "StagedGradBuckets":
+        """One bucket per refinement stage of a ``pipeline.RefinementHead`` (plus one for any other parameters)."""
+        groups = [list(st.parameters()) for st in head.refineStages]
+        seen = {id(p) for g in groups for p in g}
+        rest = [p for p in head.parameters() if id(p) not in seen]
+        if rest:
+            groups.append(rest)
+        return cls([g for g in groups if g])
+
+    def _make_hook(self, gi: int):
+        def hook(_param):
+            self._pending[gi] -= 1
+            if self._pending[gi] == 0 and self.enabled:
+                self._issue(gi)
+        return hook
+
+    def _issue(self, gi: int) -> None:
+        if self._issued[gi]:
+            return
+        self._issued[gi] = True
+        h = self.buckets[gi].all_reduce(async_op=True)
+        if h is not None:
+            self._handles.append(h)
+
+    def zero(self) -> None:
+        for gi, b in enumerate(self.buckets):
+            b.zero()
+            self._pending[gi] = len(b.params)
+            self._issued[gi] = False
+        self._handles = []
+
+    def finish(self, exchange: bool = True) -> None:
+        """Call after ``backward()``: issues what the hooks did not, then blocks the current stream on every exchange."""
+        if exchange:
+            for gi in range(len(self.buckets)):
+                self._issue(gi)
+        for h in self._handles:
+            h.wait()
+        self._handles = []
+
+    @property
+    def flat_numel(self) -> int:
+        return sum(b.flat.numel() for b in self.buckets)
+
+
 def all_reduce_losses(losses: dict) -> dict:
     """Replica losses are summed (reference gather.py:109-112)."""
-    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+    if not _dist_on():
         return losses
     keys = sorted(losses)
     buf = torch.stack([losses[k].detach().float() for k in keys])

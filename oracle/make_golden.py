@@ -181,6 +181,7 @@ def golden_graphconv_and_stages(R):
 
     # GraphConv / ResGraphConv on random features
     for name, (din, dout) in {"gc_19_16": (19, 16), "gc_16_3": (16, 3), "gc_35_24": (35, 24)}.items():
+        torch.manual_seed(100 + din)             # GraphConv.reset_parameters draws from the global RNG (layers.py:42-45)
         m = R.layers.GraphConv(din, dout)
         x = torch.randn(SV, din, generator=g)
         for dt in (torch.float32, torch.float64):

@@ -3,8 +3,9 @@
 The reference (``/root/reference``, alondj/Mesh_R-CNN_Computer_Vision_project) is pure Python / PyTorch 1.2.
 It only imports on torch 2.x behind the compatibility shims below.  This module is
 used by ``oracle/make_golden.py`` to (i) validate the oracle restatement and (ii) produce the fixtures under
-``tests/golden/``.  ``/root/reference`` does not exist on the GPU box, so nothing at test/bench run time may
-import this file; product code never does.
+``tests/golden/``.  ``/root/reference`` does not exist on the GPU box: tests never import this file there; the one run-time user is
+the reference arm of ``bench.py`` (``--impl reference``), which loads the byte-for-byte copy of the six hot-path files
+under ``oracle/_ref`` (see ``oracle/build_ref.py``).  Product code never imports it.
 
 Shims (none of them changes arithmetic):
   * stub packages ``meshRCNN`` / ``utils`` / ``data`` that skip the reference ``__init__`` files (those pull in
@@ -24,7 +25,21 @@ import types
 
 import torch
 
-REF_ROOT = os.environ.get("MESHRCNN_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root() -> str:
+    """MESHRCNN_REFERENCE if set; else the reference tree of the dev container; else ``oracle/_ref`` -- the byte-for-byte
+    copy of the six hot-path files that ``oracle/build_ref.py`` makes so that bench.py's reference arm can run on the GPU box."""
+    env = os.environ.get("MESHRCNN_REFERENCE")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/meshRCNN"):
+        return "/root/reference"
+    return os.path.join(_HERE, "_ref")
+
+
+REF_ROOT = _find_root()
 
 
 def available() -> bool:

@@ -19,6 +19,44 @@ def test_split_to_n_matches_reference_semantics():
     assert sorted(sum(parts, [])) == list(range(6))
     loads = [sum([5, 3, 8, 1, 2, 7][i] for i in p) for p in parts]
     assert abs(loads[0] - loads[1]) <= 2
+    costs = [float(c) for c in np.random.RandomState(0).randint(1500, 2600, size=64)]
+    eq = balanced_split(costs, 8, equal_counts=True)                    # snake deal: equal counts, near-equal sums
+    assert sorted(sum(eq, [])) == list(range(64)) and all(len(p) == 8 for p in eq)
+    sums = [sum(costs[i] for i in p) for p in eq]
+    naive = [sum(costs[8 * r:8 * r + 8]) for r in range(8)]
+    assert max(sums) - min(sums) < 0.25 * (max(naive) - min(naive))
+    assert balanced_split(costs[:32], 1, equal_counts=True) == [list(range(32))]
+
+
+def test_flat_grad_bucket_survives_zero_grad_set_to_none():
+    """zero_grad(set_to_none=True) drops the bucket views; all_reduce()/zero() must re-attach them instead of
+    silently exchanging a stale buffer."""
+    from meshrcnn_b200.sharding import FlatGradBucket, StagedGradBuckets
+    torch.manual_seed(0)
+    lin = torch.nn.Sequential(torch.nn.Linear(5, 4, bias=False), torch.nn.Linear(4, 2, bias=False))
+    bucket = FlatGradBucket(lin.parameters())
+    x = torch.randn(3, 5)
+    lin(x).pow(2).sum().backward()
+    want = bucket.flat.clone()
+    assert float(want.abs().sum()) > 0
+    lin.zero_grad(set_to_none=True)                                     # the views are gone
+    lin(x).pow(2).sum().backward()                                      # fresh .grad tensors, bucket untouched
+    assert bucket.sync_views() == 2
+    assert torch.allclose(bucket.flat, want) and lin[0].weight.grad.data_ptr() == bucket.flat.data_ptr()
+    bucket.zero()
+    assert float(bucket.flat.abs().sum()) == 0 and float(lin[1].weight.grad.abs().sum()) == 0
+    lin.zero_grad(set_to_none=True)
+    bucket.zero()                                                       # re-binds
+    lin(x).pow(2).sum().backward()
+    assert torch.allclose(bucket.flat, want)
+    # staged buckets: hooks count the parameters of a group; without a process group finish() is a no-op exchange
+    sb = StagedGradBuckets([list(lin[0].parameters()), list(lin[1].parameters())])
+    lin(x).pow(2).sum().backward()
+    assert sb._pending == [0, 0] and sb._issued == [True, True]
+    sb.finish()
+    assert torch.allclose(torch.cat([b.flat for b in sb.buckets]), want)
+    sb.zero()
+    assert sb._pending == [1, 1] and sb._issued == [False, False]
 
 
 def test_synthetic_inputs_are_deterministic_and_sized():
@@ -96,7 +134,7 @@ def test_sharded_losses_recombine_like_reference_dp():
 _GLOO_WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, %r)
-from meshrcnn_b200.sharding import FlatGradBucket, all_reduce_losses, split_to_n
+from meshrcnn_b200.sharding import FlatGradBucket, StagedGradBuckets, all_reduce_losses, split_to_n
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 torch.manual_seed(0)
@@ -113,6 +151,22 @@ ref.load_state_dict(lin.state_dict())
 ref(data).pow(2).sum().backward()                                       # SUM over shards == unsharded gradient
 for p, q in zip(lin.parameters(), ref.parameters()):
     assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-6), (rank, p.grad, q.grad)
+# overlapped exchange: one bucket per layer, all-reduce issued from the post-accumulate-grad hooks during backward
+lin2 = torch.nn.Sequential(torch.nn.Linear(5, 4, bias=False), torch.nn.Linear(4, 2, bias=False))
+lin2.load_state_dict(ref.state_dict())
+sb = StagedGradBuckets([list(lin2[0].parameters()), list(lin2[1].parameters())])
+for _ in range(2):                                                      # two steps: counters / handles reset correctly
+    sb.zero()
+    lin2(data[lo:hi]).pow(2).sum().backward()
+    assert sb._issued == [True, True]                                   # both exchanges were issued inside backward
+    sb.finish()
+    for p, q in zip(lin2.parameters(), ref.parameters()):
+        assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-6), (rank, p.grad, q.grad)
+sb.enabled = False                                                      # rank-local steps (time-based loops) issue nothing
+sb.zero()
+lin2(data[lo:hi]).pow(2).sum().backward()
+assert sb._issued == [False, False]
+sb.finish(exchange=False)
 # eval outputs: ragged gather with the edge ids re-offset (reference gather.py:65-92)
 from meshrcnn_b200.sharding import gather_eval_outputs
 nv = [3, 2] if rank == 0 else [4]
@@ -159,7 +213,7 @@ def test_bench_time_based_loops_issue_no_collective():
     for node in ast.walk(tree):
         if isinstance(node, ast.While) and "perf_counter" in ast.get_source_segment(src, node.test):
             for call in ast.walk(node):
-                if isinstance(call, ast.Call) and getattr(call.func, "id", None) == "step":
+                if isinstance(call, ast.Call) and "step" in (getattr(call.func, "id", None), getattr(call.func, "attr", None)):
                     kw = {k.arg: k.value for k in call.keywords}
                     assert "exchange" in kw and isinstance(kw["exchange"], ast.Constant) and kw["exchange"].value is False
                     checked += 1
@@ -167,7 +221,8 @@ def test_bench_time_based_loops_issue_no_collective():
 
 
 def test_bench_reference_arm_line_keeps_the_contract():
-    """`bench.py --impl reference` (the oracle port on the host cores) prints ONE JSON line with the contract's keys."""
+    """`bench.py --impl reference` (the reference's own CPU path from oracle/_ref, else the oracle port) prints ONE JSON
+    line with the contract's keys and the CUDA arm's workload string."""
     import json
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, timeout=600)
@@ -177,6 +232,9 @@ def test_bench_reference_arm_line_keeps_the_contract():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "meshes/s" and d["higher_is_better"] is True and d["value"] > 0
     assert d["steps"] == 1 and d["warmup"] == 0 and d["n_gpus"] == 1 and d["scaling"] == "weak" and d["vs_baseline"] is None
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    from oracle import ref_import
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_import.available() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert "BASELINE configs[1]" in d["config"]["workload"] and "1 mesh" in d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "meshes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]

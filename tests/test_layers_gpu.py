@@ -459,3 +459,70 @@ def test_overlapped_losses_equal_single_stream(lib):
     close(res[0][1], res[1][1].cpu(), what="fmap grad")
     for a, b in zip(res[0][2], res[1][2]):
         close(a, b.cpu(), what="param grad")
+
+
+def test_eval_mode_head_output_dict_vs_oracle(lib):
+    """The eval-mode output dict of the refinement-stage loop (reference shapenet_model.py:96-99 / pix3d_model.py:112-115):
+    keys, list of 4 position sets, Cubify topology -- final positions against the fp64 oracle chain; and
+    ``sharding.gather_eval_outputs`` on the real output (single process: returned unchanged)."""
+    from meshrcnn_b200 import synthetic
+    from meshrcnn_b200.pipeline import RefinementHead
+    from meshrcnn_b200.sharding import gather_eval_outputs
+    B, V = 3, 12
+    vox = synthetic.blob_voxels(B, V, 5)
+    fmap = synthetic.feature_maps(B, [synthetic.PIX3D_MAP], 5)[0] * 0.02
+    sizes = [(224, 224)] * B
+    torch.manual_seed(4)
+    head = RefinementHead("pix3d", cubify_threshold=0.2).cuda().eval()
+    with torch.no_grad():
+        for prm in head.parameters():
+            prm.mul_(0.2)
+        out = head(vox.cuda(), fmap.cuda(), sizes)
+    assert set(out) == {"vertex_positions", "edge_index", "face_index", "vertice_index", "faces", "mesh_index"}
+    o = cubify_np.cubify(vox.numpy(), 0.2)
+    assert out["vertice_index"] == o[1] and out["face_index"] == o[3] and out["mesh_index"] == [1] * B
+    assert np.array_equal(out["faces"].cpu().numpy(), o[2]) and np.array_equal(out["edge_index"].cpu().numpy(), o[4])
+    assert len(out["vertex_positions"]) == 4 and np.array_equal(out["vertex_positions"][0].cpu().numpy(), o[0])
+    cur, feats = torch.from_numpy(o[0]).double(), None
+    for s, st in enumerate(head.refineStages):
+        sd = {k: v.detach().cpu().double() for k, v in st.named_parameters()}
+        cur, feats = mesh_ops.stage_pix3d(sd, o[1], fmap.double(), torch.from_numpy(o[4]), cur, sizes, feats=feats)
+        close(out["vertex_positions"][s + 1], cur, what="eval positions of stage %d" % s)
+    assert gather_eval_outputs(out) is out
+    with pytest.raises(ValueError):
+        head.train()(vox.cuda(), fmap.cuda(), sizes)                 # training mode needs targets (shapenet_model.py:58-59)
+
+
+def test_two_devices_two_threads_like_reference_dp(lib):
+    """The reference's CustomDP drives one replica per GPU from Python threads of ONE process (dataParallel.py:33).  The
+    > 48 KB shared-memory opt-in is per device: both devices must be able to run the tcgen05 GEMM and the cell-grid k-NN
+    concurrently, and a tensor on the wrong device must be rejected."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import threading
+    from meshrcnn_b200 import functional as F_
+    res, err = {}, []
+
+    def work(i):
+        try:
+            with torch.cuda.device(i):
+                g = torch.Generator().manual_seed(i)
+                x = torch.randn(3000, 131, generator=g)
+                w = torch.randn(131, 256, generator=g)
+                y = F_.matmul(x.cuda(i), w.cuda(i))
+                p, q = torch.rand(2, 3000, 3, generator=g), torch.rand(2, 3000, 3, generator=g)
+                d = F_.knn_search(p.cuda(i), q.cuda(i), 10)
+                torch.cuda.synchronize(i)
+                res[i] = (float((y.cpu().double() - x.double() @ w.double()).abs().max()),
+                          bool(torch.equal(d[1].cpu().long(), mesh_ops.p2p_distance(p.double(), q.double()).argmin(2))))
+        except Exception as e:      # noqa: BLE001
+            err.append((i, repr(e)))
+
+    for rep in range(2):
+        ts = [threading.Thread(target=work, args=(i,)) for i in (1, 0)]        # device 1 first: the opt-in is not "done" by dev 0
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert not err, err
+        assert all(res[i][0] < 1e-3 and res[i][1] for i in (0, 1)), res
+    with torch.cuda.device(0), pytest.raises(RuntimeError):
+        F_.matmul(torch.randn(64, 32).cuda(1), torch.randn(32, 32).cuda(1))

@@ -205,8 +205,20 @@ def test_mesh_loss_matches_reference(lib, golden):
     tol = 1e-4 * want.abs() + 1e-4 * float(want.abs().max())
     frac_bad = float((err > tol).double().mean())
     assert frac_bad < 5e-3, frac_bad      # ill-conditioned rows (near-degenerate eigen-gaps) excepted, SURVEY section 7
-    # informational distance to the raw reference value (LAPACK's own signs): same order of magnitude
-    assert abs(float(nl) - float(g["f64__normal"])) < 0.5 * abs(float(g["f64__normal"]))
+    # Distance to the RAW reference value (LAPACK's own, unspecified eigenvector signs): bounded by twice the reference's
+    # own |fp32 - fp64| gap on this fixture (measured: ours 0.9 %, the reference's 1.0 %).
+    ref64, ref32 = float(g["f64__normal"]), float(g["f32__normal"])
+    own_gap = abs(ref32 - ref64)
+    assert own_gap > 0
+    assert abs(float(nl) - ref64) <= 2.0 * own_gap, (float(nl), ref64, ref32)
+
+
+def test_losses_at_bench_shape_vs_oracle(lib):
+    """Chamfer / normal / edge at the bench shape (10 000-point clouds, k = 10, two 24^3 meshes) against the fp64 oracle with
+    injected draws -- the check `python bench.py --check` runs (rtol 1e-4; normal also within 2 % of LAPACK's signs)."""
+    import bench
+    out = bench.check_bench_shape_losses(meshes=2, verbose=False)
+    assert out["points"] == 10000 and out["k"] == 10
 
 
 def test_normals_eigenvectors_vs_oracle(lib):
