@@ -117,6 +117,44 @@ int mrb_gemm_tc(const float* A, int lda, int M, int K, const void* image, int N,
 int mrb_gemm_tc_wgrad(const float* X, int ldx, const float* G, int ldg, int V, int Kin, int N, float* C0, float* C1,
                       int n_split, int ldc, void* stream);
 
+/* mrb_gemm_tc with an optional C += A * B (accumulate != 0): a product with a column concatenation [x_a | x_b] is
+ * evaluated as two calls on the parts, the second one accumulating. */
+int mrb_gemm_tc_acc(const float* A, int lda, int M, int K, const void* image, int N, float* C, int ldc, int accumulate,
+                    void* stream);
+/* mrb_gemm_tc_wgrad with the <= 4 "tail" feature columns (the 3 vertex-position columns of a stage input) taken from a
+ * separate matrix Xtail (V x n_tail, pitch ld_tail) and written to separate rows:  T0[m, 0:n_split) / T1[m, 0:N-n_split)
+ * += sum_v Xtail[v, m] * G[v, :]  -- so that dW of [pos | x] or [x | pos | ...] needs no concatenated input. */
+int mrb_gemm_tc_wgrad_split(const float* X, int ldx, const float* G, int ldg, int V, int Kin, int N, float* C0, float* C1,
+                            int n_split, int ldc, const float* Xtail, int ld_tail, int n_tail, float* T0, float* T1,
+                            void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Split-input GraphConv (csrc/graphconv2.cu) -- GraphConv.forward (reference meshRCNN/layers.py:47-68) applied to the
+ * column concatenations the stages build (layers.py:160-165,241-252,321-334) WITHOUT forming them:
+ *   z_i = y0_i + p_i Wp0 + T0[tex_i] + sum_{j in N(i)} (y1_j + T1[tex_j]) + (sum_{j in N(i)} p_j) Wp1 ;  out = relu(z) (+ residual)
+ *   y [n x 2D] = x_main [W0_x | W1_x] (mrb_gemm_tc on the dense columns), p = vertex positions with the 3 x D row blocks
+ *   wp0 / wp1 of W0 / W1, T [R x 2D] = texel rows [W0_a | W1_a] (VertexAlign fused as a row gather: tex_i = texel row of
+ *   vertex i or -1, from mrb_vert_align_texrows).  Any of the three terms may be absent (NULL).
+ *   mask (optional): ReLU mask as bits, n x ceil(D/32) words -- all the backward needs of this layer's output.
+ * mrb_gc_gather_bwd: gy[i] = [gz_i | sum_{j in N^T(i)} gz_j], gz = gout * mask;  optional gpos[i] = gy_i [Wp0 | Wp1]^T
+ *   (n x 3, overwritten) and gT[tex_i] += gy_i (gT: tex_rows x 2D, zero-filled by the call).
+ * mrb_head_fwd / _bwd: new_pos = pos + tanh(x Wx^T + pos Wp^T) with Wx = W[:, x_col:x_col+Kx], Wp = W[:, p_col:p_col+3]
+ *   of nn.Linear's 3 x Kin weight (p_col < 0: no position columns) -- layers.py:255-259,335-339; delta = the tanh output
+ *   (saved for the backward); bwd: gpre = g (1 - delta^2) (n x 3, for dW), gx = gpre Wx, gpos = g + gpre Wp.
+ */
+int mrb_vert_align_texrows(const float* pos, const int32_t* vert_mesh, const int32_t* mesh_info, int SV, int map_size,
+                           int32_t* texrow, void* stream);
+int mrb_gc_gather_fwd(const int32_t* rowptr, const int32_t* col, int n, int D, const float* y, int ld_y, const float* pos,
+                      const float* wp0, const float* wp1, const int32_t* texrow, const float* T, int relu, uint32_t* mask,
+                      const float* residual, int ld_res, float* out, int ld_out, void* stream);
+int mrb_gc_gather_bwd(const int32_t* rowptr_t, const int32_t* col_t, int n, int D, const float* gout, int ld_g,
+                      const uint32_t* mask, float* gy, const float* wp0, const float* wp1, float* gpos, const int32_t* texrow,
+                      float* gT, long long tex_rows, void* stream);
+int mrb_head_fwd(const float* x, int ld_x, int Kx, const float* pos, const float* W, int ld_w, int x_col, int p_col, int n,
+                 float* new_pos, float* delta, void* stream);
+int mrb_head_bwd(const float* g, const float* delta, const float* W, int ld_w, int x_col, int p_col, int n, int Kx,
+                 float* gpre, float* gx, int ld_gx, float* gpos, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * VertexAlign -- replaces VertexAlign.forward / single_projection / project, reference meshRCNN/layers.py:521-613,
  * with the reference's exact (non-bilinear) semantics: out[v,c] = fmap[img,c,x1,y1] * [x2>x1 && y2>y1].

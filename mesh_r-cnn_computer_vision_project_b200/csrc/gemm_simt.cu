@@ -97,12 +97,13 @@ __global__ void k_scale_rows(float* __restrict__ C, int M, int N, int ldc, float
 // ---------------------------------------------------------------------------------------------------------
 constexpr int SKINNY = 8;
 
-// C[M x N] = A[M x K] * B[N x K]^T, N <= NACC: one warp per row (coalesced reads of the long rows), lanes stride over K,
-// two rows per warp in flight, NACC accumulators per row, warp reduce
+// C[M x N] = A[M x K] * Bop[K x N], N <= NACC, Bop(k, n) = B[n * sbn + k * sbk] (either orientation of the small operand):
+// one warp per row (coalesced reads of the long rows), lanes stride over K, two rows per warp in flight, NACC accumulators
+// per row, warp reduce
 template <int NACC>
 __global__ void __launch_bounds__(256) k_skinny_nt(int M, int N, int K, const float* __restrict__ A, int lda,
-                                                   const float* __restrict__ B, int ldb, float beta, float* __restrict__ C,
-                                                   int ldc) {
+                                                   const float* __restrict__ B, int sbn, int sbk, float beta,
+                                                   float* __restrict__ C, int ldc) {
     const int m0 = (blockIdx.x * (blockDim.x >> 5) + warp_id()) * 2;
     if (m0 >= M) return;
     const int m1 = min(m0 + 1, M - 1);
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(256) k_skinny_nt(int M, int N, int K, const fl
 #pragma unroll
         for (int n = 0; n < NACC; ++n)
             if (n < N) {
-                const float b = __ldg(B + (size_t)n * ldb + k);
+                const float b = __ldg(B + (size_t)n * sbn + (size_t)k * sbk);
                 acc0[n] = fmaf(a0, b, acc0[n]);
                 acc1[n] = fmaf(a1, b, acc1[n]);
             }
@@ -136,11 +137,11 @@ __global__ void __launch_bounds__(256) k_skinny_nt(int M, int N, int K, const fl
     }
 }
 
-// C[M x N] = A[M x K] * B[K x N], K <= 8: one warp per row, lanes stride over the N columns (coalesced stores, the K values
-// of the row are broadcast loads, B comes from L1)
+// C[M x N] = A[M x K] * Bop[K x N], K <= 8, Bop(k, n) = B[k * sbk + n * sbn]: one warp per row, lanes stride over the N
+// columns (coalesced stores, the K values of the row are broadcast loads, B comes from L1)
 __global__ void __launch_bounds__(256) k_skinny_k(int M, int N, int K, const float* __restrict__ A, int lda,
-                                                  const float* __restrict__ B, int ldb, float beta, float* __restrict__ C,
-                                                  int ldc) {
+                                                  const float* __restrict__ B, int sbk, int sbn, float beta,
+                                                  float* __restrict__ C, int ldc) {
     const int m = blockIdx.x * (blockDim.x >> 5) + warp_id();
     if (m >= M) return;
     float a[SKINNY];
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(256) k_skinny_k(int M, int N, int K, const flo
         float acc = 0.f;
 #pragma unroll
         for (int k = 0; k < SKINNY; ++k)
-            if (k < K) acc = fmaf(a[k], __ldg(B + (size_t)k * ldb + n), acc);
+            if (k < K) acc = fmaf(a[k], __ldg(B + (size_t)k * sbk + (size_t)n * sbn), acc);
         float* c = C + (size_t)m * ldc + n;
         *c = (beta == 0.f) ? acc : fmaf(beta, *c, acc);
     }
@@ -158,15 +159,15 @@ __global__ void __launch_bounds__(256) k_skinny_k(int M, int N, int K, const flo
 
 // C[M x N] += A[K x M]^T * B[K x N], M <= MACC (C pre-scaled by beta): a block owns a chunk of the long K dimension; warp w
 // takes rows w, w + 8, ... of the chunk, lanes stride over the N <= 256 columns (coalesced), the 8 warps' partial sums are
-// combined in shared memory and added to C with one atomic per element and block.
+// combined in shared memory one output row at a time (every index into acc[][] is a compile-time constant, so the
+// partial sums stay in registers) and added to C with one atomic per element and block.
 template <int MACC>
 __global__ void __launch_bounds__(256) k_skinny_tn(int M, int N, int K, const float* __restrict__ A, int lda,
-                                                   const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
-                                                   int rows_per_block) {
-    constexpr int JMAX = 8;                                // N <= 256
-    __shared__ float red[8][MACC][32 * JMAX / 4 + 1];      // reused per column quarter (see below)
+                                                   const float* __restrict__ B, int ldb, float* __restrict__ C, int scm,
+                                                   int scn, int rows_per_block) {
+    constexpr int JMAX = 8;                                // N <= 256;  C(m, n) = C[m * scm + n * scn]
+    __shared__ float red[8][32 * JMAX];
     const int k0 = blockIdx.x * rows_per_block, k1 = min(K, k0 + rows_per_block);
-    const int nj = (N + 31) >> 5;
     float acc[MACC][JMAX];
 #pragma unroll
     for (int m = 0; m < MACC; ++m)
@@ -179,35 +180,25 @@ __global__ void __launch_bounds__(256) k_skinny_tn(int M, int N, int K, const fl
 #pragma unroll
         for (int j = 0; j < JMAX; ++j) {
             const int n = j * 32 + lane_id();
-            if (j < nj && n < N) {
+            if (n < N) {
                 const float b = B[(size_t)k * ldb + n];
 #pragma unroll
                 for (int m = 0; m < MACC; ++m) acc[m][j] = fmaf(a[m], b, acc[m][j]);
             }
         }
     }
-    // combine the 8 warps, two column blocks (64 columns) at a time
-    for (int jb = 0; jb < nj; jb += 2) {
+#pragma unroll
+    for (int m = 0; m < MACC; ++m) {
+        if (m >= M) break;                                 // uniform
         __syncthreads();
 #pragma unroll
-        for (int m = 0; m < MACC; ++m)
-#pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-                float v = 0.f;
-#pragma unroll
-                for (int j = 0; j < JMAX; ++j)
-                    if (j == jb + jj) v = acc[m][j];
-                red[warp_id()][m][jj * 32 + lane_id()] = v;
-            }
+        for (int j = 0; j < JMAX; ++j) red[warp_id()][j * 32 + lane_id()] = acc[m][j];
         __syncthreads();
-        for (int e = threadIdx.x; e < MACC * 64; e += blockDim.x) {
-            const int m = e / 64, c = e % 64, n = jb * 32 + c;
-            if (m < M && n < N) {
-                float v = 0.f;
+        for (int n = threadIdx.x; n < N; n += blockDim.x) {
+            float v = 0.f;
 #pragma unroll
-                for (int w = 0; w < 8; ++w) v += red[w][m][c];
-                atomicAdd(C + (size_t)m * ldc + n, v);
-            }
+            for (int w = 0; w < 8; ++w) v += red[w][n];
+            atomicAdd(C + (size_t)m * scm + (size_t)n * scn, v);
         }
     }
 }
@@ -224,20 +215,29 @@ extern "C" int mrb_sgemm(int transA, int transB, int M, int N, int K, const floa
     MRB_REQUIRE(M >= 0 && N >= 0 && K >= 0, "sgemm: negative dimension");
     if (M == 0 || N == 0) return MRB_OK;
     cudaStream_t s = (cudaStream_t)stream_;
-    if (K > 0 && !transA && transB && N <= SKINNY) {
-        if (N <= 4) k_skinny_nt<4><<<ceil_div(M, 16), 256, 0, s>>>(M, N, K, A, lda, B, ldb, beta, C, ldc);
-        else k_skinny_nt<SKINNY><<<ceil_div(M, 16), 256, 0, s>>>(M, N, K, A, lda, B, ldb, beta, C, ldc);
+    if (K > 0 && !transA && N <= SKINNY && K > SKINNY) {            // tall A times a skinny B (either orientation)
+        const int sbn = transB ? ldb : 1, sbk = transB ? 1 : ldb;
+        if (N <= 4) k_skinny_nt<4><<<ceil_div(M, 16), 256, 0, s>>>(M, N, K, A, lda, B, sbn, sbk, beta, C, ldc);
+        else k_skinny_nt<SKINNY><<<ceil_div(M, 16), 256, 0, s>>>(M, N, K, A, lda, B, sbn, sbk, beta, C, ldc);
         return check_launch("sgemm");
     }
-    if (K > 0 && !transA && !transB && K <= SKINNY) {
-        k_skinny_k<<<ceil_div(M, 8), 256, 0, s>>>(M, N, K, A, lda, B, ldb, beta, C, ldc);
+    if (K > 0 && !transA && K <= SKINNY) {                          // outer-product-like: K <= 8
+        const int sbk = transB ? 1 : ldb, sbn = transB ? ldb : 1;
+        k_skinny_k<<<ceil_div(M, 8), 256, 0, s>>>(M, N, K, A, lda, B, sbk, sbn, beta, C, ldc);
         return check_launch("sgemm");
     }
-    if (K > 0 && transA && !transB && M <= SKINNY && N <= 256) {
+    if (K > 0 && transA && !transB && M <= SKINNY && N <= 256) {    // reduction over the long K into a skinny-row C
         k_scale_rows<<<(unsigned)ceil_div64((long long)M * N, 256), 256, 0, s>>>(C, M, N, ldc, beta);
         const int rpb = max(64, ceil_div(K, 4 * kNumSMs));
-        if (M <= 4) k_skinny_tn<4><<<ceil_div(K, rpb), 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, rpb);
-        else k_skinny_tn<SKINNY><<<ceil_div(K, rpb), 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, rpb);
+        if (M <= 4) k_skinny_tn<4><<<ceil_div(K, rpb), 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, 1, rpb);
+        else k_skinny_tn<SKINNY><<<ceil_div(K, rpb), 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, 1, rpb);
+        return check_launch("sgemm");
+    }
+    if (K > 0 && transA && !transB && N <= SKINNY && M <= 256) {    // same with a skinny-column C: C^T = B^T A
+        k_scale_rows<<<(unsigned)ceil_div64((long long)M * N, 256), 256, 0, s>>>(C, M, N, ldc, beta);
+        const int rpb = max(64, ceil_div(K, 4 * kNumSMs));
+        if (N <= 4) k_skinny_tn<4><<<ceil_div(K, rpb), 256, 0, s>>>(N, M, K, B, ldb, A, lda, C, 1, ldc, rpb);
+        else k_skinny_tn<SKINNY><<<ceil_div(K, rpb), 256, 0, s>>>(N, M, K, B, ldb, A, lda, C, 1, ldc, rpb);
         return check_launch("sgemm");
     }
     const int gx = ceil_div(N, BN), gy = ceil_div(M, BM);

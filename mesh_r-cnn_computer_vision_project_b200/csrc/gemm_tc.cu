@@ -553,7 +553,9 @@ struct ParamsTN {
     int chunks_per_split;
     float* C0; float* C1;         // columns [0, n_split) -> C0 (ld ldc), [n_split, N) -> C1
     int n_split, ldc;
-    int tail;                     // 0..TN_TAIL_MAX extra rows [Kin, Kin + tail) of C, accumulated on the CUDA cores by tile 0
+    int tail;                     // 0..TN_TAIL_MAX extra feature columns, accumulated on the CUDA cores by tile 0:
+    const float* Xtail; int ld_tail;   //   T[m, j] += sum_v Xtail[v * ld_tail + m] * G[v, j]   (m < tail)
+    float* T0; float* T1;              //   columns [0, n_split) -> T0 + m * ldc, [n_split, N) -> T1 + m * ldc
 };
 constexpr int TN_TAIL_MAX = 4;
 
@@ -624,7 +626,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tn(ParamsTN p) {
                     const int v = min(v0 + t, p.V - 1);
 #pragma unroll
                     for (int m = 0; m < TN_TAIL_MAX; ++m)
-                        if (m < ntail) xtail[t * TN_TAIL_MAX + m] = __ldg(p.X + (size_t)v * p.ldx + p.Kin + m);
+                        if (m < ntail) xtail[t * TN_TAIL_MAX + m] = __ldg(p.Xtail + (size_t)v * p.ld_tail + m);
 #pragma unroll
                     for (int mb = 0; mb < 4; ++mb)
                         x[mb * 4 + t] = __ldg(p.X + (size_t)v * p.ldx + min(i0 + mb * 32 + lane, p.Kin - 1));
@@ -720,8 +722,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tn(ParamsTN p) {
                     float sum = 0.f;
 #pragma unroll
                     for (int w = 0; w < TN_PROD_WARPS; ++w) sum += red[(w * TN_TAIL_MAX + m) * 256 + j];
-                    float* dst = (j < p.n_split) ? p.C0 + (size_t)(p.Kin + m) * p.ldc + j
-                                                 : p.C1 + (size_t)(p.Kin + m) * p.ldc + (j - p.n_split);
+                    float* dst = (j < p.n_split) ? p.T0 + (size_t)m * p.ldc + j : p.T1 + (size_t)m * p.ldc + (j - p.n_split);
                     atomicAdd(dst, sum);
                 }
             }
@@ -798,15 +799,15 @@ extern "C" int mrb_gemm_tc_pack_graphconv(const float* w0, const float* w1, int 
     return check_launch("gemm_tc_pack_graphconv");
 }
 
-extern "C" int mrb_gemm_tc(const float* A, int lda, int M, int K, const void* image, int N, float* C, int ldc,
-                           void* stream_) {
-    MRB_REQUIRE(A && image && C, "gemm_tc: null pointer");
-    MRB_REQUIRE(M >= 0 && K > 0 && N > 0 && lda >= K && ldc >= N, "gemm_tc: bad shape M=%d K=%d N=%d lda=%d ldc=%d", M, K, N,
+static int launch_gemm_tc(const float* A, int lda, int M, int K, const void* image, int N, float* C, int ldc, int accumulate,
+                          void* stream_, const char* what) {
+    MRB_REQUIRE(A && image && C, "%s: null pointer", what);
+    MRB_REQUIRE(M >= 0 && K > 0 && N > 0 && lda >= K && ldc >= N, "%s: bad shape M=%d K=%d N=%d lda=%d ldc=%d", what, M, K, N,
                 lda, ldc);
-    MRB_REQUIRE(((uintptr_t)image & 15) == 0, "gemm_tc: image must be 16-byte aligned");
+    MRB_REQUIRE(((uintptr_t)image & 15) == 0, "%s: image must be 16-byte aligned", what);
     if (M == 0) return MRB_OK;
     static SmemOptIn optin;
-    if (int rc = ensure_dynamic_smem(k_gemm_tc, TC_SMEM_LIMIT, optin, "gemm_tc")) return rc;
+    if (int rc = ensure_dynamic_smem(k_gemm_tc, TC_SMEM_LIMIT, optin, what)) return rc;
     const Plan pl = make_plan(K, N);
     // The tensor-core fp32 accumulate truncates, so the error of an accumulator grows with the number of MMAs chained
     // into it.  K is therefore processed in segments of SEG chunks (1024 columns); every segment is a full pass whose
@@ -826,32 +827,43 @@ extern "C" int mrb_gemm_tc(const float* A, int lda, int M, int K, const void* im
         p.acc_bufs = (2 * p.nacc * pl.tmem_cols <= 512) ? 2 : 1;
         p.mtiles = ceil_div(M, BM);
         p.ntiles = pl.ntiles;
-        p.accumulate = c0 > 0;
+        p.accumulate = (c0 > 0) || accumulate;
         p.C = C; p.ldc = ldc;
         p.stages = pl.stages; p.stage_bytes = pl.stage_bytes;
         const int grid = min(p.mtiles * p.ntiles, kNumSMs);
         k_gemm_tc<<<grid, TC_THREADS, pl.stages * pl.stage_bytes + EPI_BYTES + 1024 + 256, (cudaStream_t)stream_>>>(p);
     }
-    return check_launch("gemm_tc");
+    return check_launch(what);
 }
 
-extern "C" int mrb_gemm_tc_wgrad(const float* X, int ldx, const float* G, int ldg, int V, int Kin, int N, float* C0,
-                                 float* C1, int n_split, int ldc, void* stream_) {
-    MRB_REQUIRE(X && G && C0, "gemm_tc_wgrad: null pointer");
-    MRB_REQUIRE(N % 32 == 0 && N >= 32 && N <= NT_MAX, "gemm_tc_wgrad: N must be a multiple of 32 in [32, 256], got %d", N);
-    MRB_REQUIRE(n_split % 32 == 0 && n_split > 0 && n_split <= N && (n_split == N || C1), "gemm_tc_wgrad: bad column split");
+extern "C" int mrb_gemm_tc(const float* A, int lda, int M, int K, const void* image, int N, float* C, int ldc,
+                           void* stream_) {
+    return launch_gemm_tc(A, lda, M, K, image, N, C, ldc, 0, stream_, "gemm_tc");
+}
+
+extern "C" int mrb_gemm_tc_acc(const float* A, int lda, int M, int K, const void* image, int N, float* C, int ldc,
+                               int accumulate, void* stream_) {
+    return launch_gemm_tc(A, lda, M, K, image, N, C, ldc, accumulate != 0, stream_, "gemm_tc_acc");
+}
+
+static int launch_wgrad(const float* X, int ldx, const float* G, int ldg, int V, int Kin, int N, float* C0, float* C1,
+                        int n_split, int ldc, const float* Xtail, int ld_tail, int n_tail, float* T0, float* T1,
+                        void* stream_, const char* what) {
+    MRB_REQUIRE(X && G && C0, "%s: null pointer", what);
+    MRB_REQUIRE(N % 32 == 0 && N >= 32 && N <= NT_MAX, "%s: N must be a multiple of 32 in [32, 256], got %d", what, N);
+    MRB_REQUIRE(n_split % 32 == 0 && n_split > 0 && n_split <= N && (n_split == N || C1), "%s: bad column split", what);
     MRB_REQUIRE(ldc % 4 == 0 && ((uintptr_t)C0 & 15) == 0 && (!C1 || ((uintptr_t)C1 & 15) == 0),
-                "gemm_tc_wgrad: C rows must be 16-byte aligned");
-    MRB_REQUIRE(Kin > 0 && V >= 0 && ldx >= Kin && ldg >= N, "gemm_tc_wgrad: bad shape");
+                "%s: C rows must be 16-byte aligned", what);
+    MRB_REQUIRE(Kin > 0 && V >= 0 && ldx >= Kin && ldg >= N, "%s: bad shape", what);
+    MRB_REQUIRE(n_tail >= 0 && n_tail <= TN_TAIL_MAX && (n_tail == 0 || (Xtail && T0 && ld_tail >= n_tail && (n_split == N || T1))),
+                "%s: bad tail (0..%d extra columns)", what, TN_TAIL_MAX);
     if (V == 0) return MRB_OK;
     static SmemOptIn optin8, optin4;
-    if (int rc = ensure_dynamic_smem(k_gemm_tn<8, 1>, SMEM_BYTES, optin8, "gemm_tc_wgrad")) return rc;
-    if (int rc = ensure_dynamic_smem(k_gemm_tn<4, 2>, SMEM_BYTES, optin4, "gemm_tc_wgrad")) return rc;
-    const int tail = (Kin > BM && Kin % BM <= TN_TAIL_MAX) ? Kin % BM : 0;   // e.g. the 3 position columns of a stage input
-    Kin -= tail;
+    if (int rc = ensure_dynamic_smem(k_gemm_tn<8, 1>, SMEM_BYTES, optin8, what)) return rc;
+    if (int rc = ensure_dynamic_smem(k_gemm_tn<4, 2>, SMEM_BYTES, optin4, what)) return rc;
     ParamsTN p;
     p.X = X; p.ldx = ldx; p.G = G; p.ldg = ldg; p.V = V; p.Kin = Kin; p.N = N; p.C0 = C0; p.C1 = C1; p.n_split = n_split;
-    p.ldc = ldc; p.tail = tail;
+    p.ldc = ldc; p.tail = n_tail; p.Xtail = Xtail; p.ld_tail = ld_tail; p.T0 = T0; p.T1 = T1;
     const int mtiles = ceil_div(Kin, BM);
     const int total_chunks = ceil_div(V, BK);
     int splits = max(1, min(total_chunks, kNumSMs / mtiles));
@@ -859,5 +871,22 @@ extern "C" int mrb_gemm_tc_wgrad(const float* X, int ldx, const float* G, int ld
     splits = ceil_div(total_chunks, p.chunks_per_split);
     if (N <= 128) k_gemm_tn<4, 2><<<dim3(mtiles, splits), TN_THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(p);
     else k_gemm_tn<8, 1><<<dim3(mtiles, splits), TN_THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(p);
-    return check_launch("gemm_tc_wgrad");
+    return check_launch(what);
+}
+
+extern "C" int mrb_gemm_tc_wgrad(const float* X, int ldx, const float* G, int ldg, int V, int Kin, int N, float* C0,
+                                 float* C1, int n_split, int ldc, void* stream_) {
+    MRB_REQUIRE(X && C0 && Kin > 0, "gemm_tc_wgrad: bad arguments");
+    // the 3 position columns of a concatenated stage input (Kin = 128 k + 3): rows [Kin - tail, Kin) go through the tail path
+    const int tail = (Kin > BM && Kin % BM <= TN_TAIL_MAX) ? Kin % BM : 0;
+    const int Km = Kin - tail;
+    return launch_wgrad(X, ldx, G, ldg, V, Km, N, C0, C1, n_split, ldc, X + Km, ldx, tail, C0 + (size_t)Km * ldc,
+                        C1 ? C1 + (size_t)Km * ldc : nullptr, stream_, "gemm_tc_wgrad");
+}
+
+extern "C" int mrb_gemm_tc_wgrad_split(const float* X, int ldx, const float* G, int ldg, int V, int Kin, int N, float* C0,
+                                       float* C1, int n_split, int ldc, const float* Xtail, int ld_tail, int n_tail, float* T0,
+                                       float* T1, void* stream_) {
+    return launch_wgrad(X, ldx, G, ldg, V, Kin, N, C0, C1, n_split, ldc, Xtail, ld_tail, n_tail, T0, T1, stream_,
+                        "gemm_tc_wgrad_split");
 }

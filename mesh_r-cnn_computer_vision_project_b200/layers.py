@@ -69,6 +69,13 @@ class VertexAlign(nn.Module):
         return F_.vert_align(img_features, vertex_positions, vertices_per_mesh, image_sizes, mesh_index)
 
 
+# Stage inputs are column concatenations [features | position | aligned features] (reference layers.py:160-165,241-252,
+# 321-334).  True: the layers consume them as parts (split-input GraphConv, csrc/graphconv2.cu: dense blocks on the tensor
+# cores, the 3 position columns in the gather epilogue, VertexAlign as a texel-row gather, fused tanh head) and nothing is
+# concatenated.  False: the literal evaluation (concatenate, then the generic kernels) -- kept for the parity tests.
+FUSE_STAGE_INPUTS = True
+
+
 class GraphConv(nn.Module):
     """f'_i = ReLU(W0 f_i + sum_{j in N(i)} W1 f_j)  -- reference meshRCNN/layers.py:25-68.
     Parameters ``w0`` / ``w1`` are stored in x out and initialised U(+-1/sqrt(in)) (:42-45); no bias; the ReLU
@@ -85,8 +92,16 @@ class GraphConv(nn.Module):
         self.w0.data.uniform_(-bound, bound)
         self.w1.data.uniform_(-bound, bound)
 
-    def forward(self, vertex_features: Tensor, vertex_adjacency: Tensor) -> Tensor:
-        return F_.graph_conv(vertex_features, vertex_adjacency, self.w0, self.w1)
+    def forward(self, vertex_features, vertex_adjacency: Tensor, residual: Optional[Tensor] = None) -> Tensor:
+        """``vertex_features``: SV x in_features (the reference signature), or -- an extension used by the stage classes -- a
+        list of parts ``[("x", dense block) | ("pos", SV x 3) | ("tex", functional.TexelTerm), ...]`` standing for their
+        column concatenation, which is then never materialised (functional.graph_conv_parts)."""
+        if isinstance(vertex_features, (list, tuple)):
+            return F_.graph_conv_parts(vertex_features, vertex_adjacency, self.w0, self.w1, residual)
+        if FUSE_STAGE_INPUTS and self.w0.shape[1] % 4 == 0:
+            return F_.graph_conv_parts([("x", vertex_features)], vertex_adjacency, self.w0, self.w1, residual)
+        out = F_.graph_conv(vertex_features, vertex_adjacency, self.w0, self.w1)
+        return out if residual is None else out + residual
 
 
 class _BiasFreeLinear(nn.Linear):
@@ -109,10 +124,15 @@ class ResGraphConv(nn.Module):
         self.conv1 = GraphConv(out_features, out_features)
         self.projection = _BiasFreeLinear(in_features, out_features) if in_features != out_features else nn.Identity()
 
-    def forward(self, vertex_features: Tensor, vertex_adjacency: Tensor) -> Tensor:
-        skip = self.projection(vertex_features)
-        out = self.conv1(self.conv0(vertex_features, vertex_adjacency), vertex_adjacency)
-        return skip + out
+    def forward(self, vertex_features, vertex_adjacency: Tensor) -> Tensor:
+        """``vertex_features``: SV x in_features or a list of parts (see ``GraphConv.forward``)."""
+        if isinstance(vertex_features, (list, tuple)):
+            dense = [t for _, t in vertex_features]
+            skip = self.projection(dense[0] if len(dense) == 1 else F_.concat_cols(dense))
+        else:
+            skip = self.projection(vertex_features)
+        # the skip connection is added in the epilogue of conv1's gather kernel
+        return self.conv1(self.conv0(vertex_features, vertex_adjacency), vertex_adjacency, residual=skip)
 
 
 def _default_mesh_index(mesh_index, image_sizes):
@@ -138,13 +158,25 @@ def _align_and_project(align: "VertexAlign", linear: nn.Linear, img_feature_maps
 
 
 def _stage_input(vertex_positions, pooled, vertex_features, use_input_features):
-    parts = [vertex_positions, pooled]
+    """[features? | positions | pooled] (reference layers.py:160-165) -- as parts, or concatenated (literal mode)."""
     if vertex_features is not None:
         assert use_input_features
-        parts = [vertex_features] + parts
     else:
         assert not use_input_features
+    if FUSE_STAGE_INPUTS:
+        parts = [("pos", vertex_positions), ("tex", pooled) if isinstance(pooled, F_.TexelTerm) else ("x", pooled)]
+        return ([("x", vertex_features)] if vertex_features is not None else []) + parts
+    parts = [vertex_positions, pooled]
+    if vertex_features is not None:
+        parts = [vertex_features] + parts
     return F_.concat_cols(parts)
+
+
+def _with_pos(vertex_positions, x):
+    """[positions | x] (reference layers.py:245,250,327,332)."""
+    if FUSE_STAGE_INPUTS:
+        return [("pos", vertex_positions), ("x", x)]
+    return F_.concat_cols([vertex_positions, x])
 
 
 class ResVertixRefineShapenet(nn.Module):
@@ -202,8 +234,10 @@ class VertixRefineShapeNet(nn.Module):
                                        image_sizes, mesh_index)
         x = _stage_input(vertex_positions, projected, vertex_features, self.use_input_features)
         x = self.graphConv0(x, vertex_adjacency)
-        x = self.graphConv1(F_.concat_cols([vertex_positions, x]), vertex_adjacency)
-        x = self.graphConv2(F_.concat_cols([vertex_positions, x]), vertex_adjacency)
+        x = self.graphConv1(_with_pos(vertex_positions, x), vertex_adjacency)
+        x = self.graphConv2(_with_pos(vertex_positions, x), vertex_adjacency)
+        if FUSE_STAGE_INPUTS:
+            return F_.position_head(x, vertex_positions, self.linear1.weight, pos_first=None), x
         delta = self.tanh(self.linear1(x))
         return vertex_positions + delta, x
 
@@ -227,10 +261,20 @@ class VertixRefinePix3D(nn.Module):
                 vertex_positions: Tensor, image_sizes: List, mesh_index: List[int] = None,
                 vertex_features: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
         mesh_index = _default_mesh_index(mesh_index, image_sizes)
-        aligned = self.vertAlign([back_bone_features], vertex_positions, vertice_index, image_sizes, mesh_index)
+        if FUSE_STAGE_INPUTS and self.graphConv0.w0.shape[1] % 4 == 0:
+            # VertexAlign stays factored: graphConv0 projects the texels and gathers rows (functional.TexelTerm)
+            if self.vertAlign.training:                             # the checks of VertexAlign.forward (layers.py:528-532)
+                assert len(vertice_index) == len(image_sizes)
+                assert list(mesh_index) == [1 for _ in image_sizes]
+            assert len(mesh_index) == len(image_sizes)
+            aligned = F_.TexelTerm(back_bone_features, vertex_positions, vertice_index, image_sizes, mesh_index)
+        else:
+            aligned = self.vertAlign([back_bone_features], vertex_positions, vertice_index, image_sizes, mesh_index)
         x = _stage_input(vertex_positions, aligned, vertex_features, self.use_input_features)
         x = self.graphConv0(x, vertex_adjacency)
-        x = self.graphConv1(F_.concat_cols([vertex_positions, x]), vertex_adjacency)
-        x = self.graphConv2(F_.concat_cols([vertex_positions, x]), vertex_adjacency)
+        x = self.graphConv1(_with_pos(vertex_positions, x), vertex_adjacency)
+        x = self.graphConv2(_with_pos(vertex_positions, x), vertex_adjacency)
+        if FUSE_STAGE_INPUTS:
+            return F_.position_head(x, vertex_positions, self.linear.weight, pos_first=True), x
         delta = self.tanh(self.linear(F_.concat_cols([vertex_positions, x])))
         return vertex_positions + delta, x

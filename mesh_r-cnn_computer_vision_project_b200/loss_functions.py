@@ -56,7 +56,9 @@ def mesh_loss(vertex_positions_pred: Tensor, mesh_faces_pred: Tensor, pred_adjac
     cloud_pred, _ = F_.sample_points(vertex_positions_pred, mesh_faces_pred, vertices_per_sample_pred,
                                      faces_per_sample_pred, n, **rnd_pred)                          # :51-53
     pos_gt, faces_gt = batch.meshes
-    cloud_gt, _ = F_.sample_points(pos_gt, faces_gt, batch.vertice_index, batch.face_index, n, **rnd_gt)   # :57-59
+    # :57-59 -- the GT cloud is re-sampled at every call like the reference; the area CDF of the static GT meshes is
+    # computed once per batch object (device-resident cache, functional.cached_face_cdf)
+    cloud_gt, _ = F_.sample_points(pos_gt, faces_gt, batch.vertice_index, batch.face_index, n, cdf_owner=batch, **rnd_gt)
 
     loss_p, loss_gt, idx_p, idx_gt, knn_p, knn_gt = F_.chamfer_knn(cloud_pred, cloud_gt, k)         # :62-65,141
     chamfer_loss = (loss_p + loss_gt) / point_cloud_size                                            # :66

@@ -1,37 +1,53 @@
-"""cProfile view of the host side of one bench step (Python + ctypes + autograd dispatch), GPU work left asynchronous."""
-import sys, os, time, cProfile, pstats, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+"""Host side of one headline step: issue time per step with the GPU idle at the start of every step (the e2e situation),
+allocator activity per step, and a cProfile listing.      python scripts/profile_host.py [steps]"""
+import cProfile, os, pstats, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
 import bench
-from meshrcnn_b200.layers import Cubify
-from meshrcnn_b200.mesh_sampling import normalize_mesh
-from meshrcnn_b200.pipeline import MeshTargets, RefinementHead, weighted_loss
-from meshrcnn_b200.sharding import FlatGradBucket
-dev = torch.device("cuda", 0)
-B = 32
-vox_h, fmap_h, gt_vox_h = bench.make_inputs(B, 0)
-sizes = [(224, 224)] * B
-torch.manual_seed(1)
-head = RefinementHead("pix3d", cubify_threshold=0.2).to(dev).train()
-bucket = FlatGradBucket(head.parameters())
-gv, gvi, gfaces, gfi, _ = Cubify(0.5)(gt_vox_h.to(dev))
-gt = MeshTargets(torch.cat([normalize_mesh(v) for v in gv.split(gvi)]), gfaces, gvi, gfi)
-vox_d = vox_h.to(dev); fmap_d = fmap_h.to(dev).requires_grad_()
-def step():
-    bucket.zero(); fmap_d.grad = None
-    losses = head(vox_d, fmap_d, sizes, gt)
-    weighted_loss(losses).backward()
-for _ in range(5): step()
+from meshrcnn_b200 import build, _lib
+build.build(); _lib.load()
+dev = torch.device("cuda", 0); torch.cuda.set_device(dev)
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+wl = bench.HeadWorkload("pix3d", dev, 0, 1)
+for _ in range(20):
+    wl.step()
 torch.cuda.synchronize()
-N = 20
-t0 = time.perf_counter()
-for _ in range(N): step()
-t1 = time.perf_counter()
-torch.cuda.synchronize()
-t2 = time.perf_counter()
-print("host time per step (launch side only): %.3f ms; incl. final sync: %.3f ms" % ((t1 - t0) / N * 1e3, (t2 - t0) / N * 1e3))
-pr = cProfile.Profile()
-pr.enable()
-for _ in range(N): step()
-pr.disable()
-torch.cuda.synchronize()
-st = pstats.Stats(pr); st.sort_stats("tottime").print_stats(35)
+
+def host_times(fn, n):
+    out = []
+    for _ in range(n):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter(); fn(); t1 = time.perf_counter()
+        torch.cuda.synchronize(); t2 = time.perf_counter()
+        out.append(((t1 - t0) * 1e3, (t2 - t0) * 1e3))
+    out.sort()
+    return out[len(out) // 2]
+
+s0 = torch.cuda.memory_stats(dev)
+print("host issue / total ms per step (median), staged buckets + hooks: %.3f / %.3f" % host_times(wl.step, N))
+s1 = torch.cuda.memory_stats(dev)
+print("cudaMalloc segments allocated during %d steps: %d; allocations per step: %.0f" % (
+    N, s1["segment.all.allocated"] - s0["segment.all.allocated"], (s1["allocation.all.allocated"] - s0["allocation.all.allocated"]) / N))
+import gc
+gc.collect(); gc.disable()
+print("same with gc disabled: %.3f / %.3f" % host_times(wl.step, N))
+gc.enable()
+wl.head.overlap_losses = False
+print("single stream (no loss-stream overlap): %.3f / %.3f" % host_times(wl.step, N))
+wl.head.overlap_losses = True
+# count ATen vs own launches with the profiler-free method: torch.profiler is heavy; use _lib.launch_count for own kernels
+l0 = _lib.launch_count; wl.step(); print("own kernel launches per step:", _lib.launch_count - l0)
+pr = cProfile.Profile(); pr.enable()
+for _ in range(N):
+    wl.step()
+pr.disable(); torch.cuda.synchronize()
+st = pstats.Stats(pr); st.sort_stats("tottime").print_stats(40)
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    wl.step(); torch.cuda.synchronize()
+ka = prof.key_averages()
+rows = sorted([(k.key, k.count, getattr(k, "device_time_total", 0.0)) for k in ka if getattr(k, "device_time_total", 0) > 0 and k.count], key=lambda r: -r[2])
+print("GPU kernels of one step (torch.profiler): name, launches, total us")
+for r in rows[:60]:
+    print("  %-90s %4d %9.1f" % (r[0][:90], r[1], r[2]))

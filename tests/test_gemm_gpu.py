@@ -78,8 +78,39 @@ def test_tc_wgrad(lib, V, Kin, N, split):
     assert err <= 1e-5 * float(want.abs().max()), (V, Kin, N, err, float(want.abs().max()))
 
 
+def test_tc_gemm_accumulate_and_wgrad_split(lib):
+    """mrb_gemm_tc_acc (C += A B: a product with [x_a | x_b] as two calls) and mrb_gemm_tc_wgrad_split (the 3 position
+    columns from their own matrix, written to their own rows of dW0 | dW1)."""
+    from meshrcnn_b200 import _lib, functional as F_
+    g = torch.Generator().manual_seed(11)
+    M, Ka, Kb, N = 3000, 128, 64, 256
+    xa, xb = torch.randn(M, Ka, generator=g), torch.randn(M, Kb, generator=g)
+    w = torch.randn(Ka + Kb, N, generator=g)
+    wd, xad, xbd = w.cuda(), xa.cuda(), xb.cuda()
+    c = torch.empty(M, N, device="cuda")
+    lib_ = _lib.load()
+    for i, (x, r, K) in enumerate(((xad, 0, Ka), (xbd, Ka, Kb))):
+        img = torch.empty(lib_.mrb_gemm_tc_image_bytes(K, N), dtype=torch.uint8, device="cuda")
+        _lib.call("mrb_gemm_tc_pack", wd.data_ptr() + 4 * r * N, None, N, 1, 0, 0, K, N, _lib.ptr(img))
+        _lib.call("mrb_gemm_tc_acc", _lib.ptr(x), K, M, K, _lib.ptr(img), N, _lib.ptr(c), N, i)
+    want = torch.cat([xa, xb], 1).double() @ w.double()
+    assert float((c.cpu().double() - want).norm() / want.norm()) <= 2e-6
+    # wgrad: dW rows [3, 131) from x (128 wide), rows [0, 3) from pos -- the layout of a [pos | x] layer
+    V, D = 4097, 128
+    x, pos, gy = torch.randn(V, 128, generator=g), torch.randn(V, 3, generator=g), torch.randn(V, 2 * D, generator=g)
+    xd, pd, gd = x.cuda(), pos.cuda(), gy.cuda()
+    gw = torch.zeros(2, 131, D, device="cuda")
+    g0, g1 = gw.data_ptr(), gw.data_ptr() + 4 * 131 * D
+    _lib.call("mrb_gemm_tc_wgrad_split", _lib.ptr(xd), 128, _lib.ptr(gd), 2 * D, V, 128, 2 * D, g0 + 4 * 3 * D, g1 + 4 * 3 * D, D, D,
+              _lib.ptr(pd), 3, 3, g0, g1)
+    want = torch.cat([pos, x], 1).double().t() @ gy.double()
+    got = torch.cat([gw[0], gw[1]], 1).cpu().double()
+    assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max())
+
+
 @pytest.mark.parametrize("ta,tb,M,N,K", [(0, 1, 5000, 3, 131), (0, 0, 5000, 131, 3), (1, 0, 3, 131, 5000), (0, 1, 77, 8, 40),
-                                         (1, 0, 8, 300, 999), (0, 0, 100, 50, 70), (1, 1, 33, 65, 129), (1, 0, 131, 128, 4000)])
+                                         (1, 0, 8, 300, 999), (0, 0, 100, 50, 70), (1, 1, 33, 65, 129), (1, 0, 131, 128, 4000),
+                                         (0, 0, 5000, 3, 128), (0, 1, 5000, 128, 3), (1, 0, 128, 3, 5000), (1, 0, 200, 6, 3000)])
 def test_sgemm_simt_all_paths(lib, ta, tb, M, N, K):
     """Exact-fp32 CUDA-core GEMM incl. the skinny special cases of the 3-wide heads, with beta accumulation."""
     from meshrcnn_b200 import _lib

@@ -526,3 +526,141 @@ def test_two_devices_two_threads_like_reference_dp(lib):
         assert all(res[i][0] < 1e-3 and res[i][1] for i in (0, 1)), res
     with torch.cuda.device(0), pytest.raises(RuntimeError):
         F_.matmul(torch.randn(64, 32).cuda(1), torch.randn(32, 32).cuda(1))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# split-input GraphConv (csrc/graphconv2.cu): parts vs the literal concatenation vs the fp64 oracle
+# ---------------------------------------------------------------------------------------------------------------
+def _parts_case(with_feat, with_tex, D=32, seed=3):
+    from meshrcnn_b200 import synthetic
+    import meshrcnn_b200.layers as L
+    B, V = 3, 10
+    vox = synthetic.blob_voxels(B, V, seed)
+    verts, v_index, faces, f_index, adj = L.Cubify(0.2)(vox.cuda())
+    SV = verts.shape[0]
+    g = torch.Generator().manual_seed(seed)
+    pos = synthetic.in_frustum_positions(SV, 224, seed)
+    feat = torch.randn(SV, 48, generator=g) if with_feat else None
+    fmap = synthetic.feature_maps(B, [(20, 12, 12)], seed)[0] if with_tex else None
+    K = (48 if with_feat else 0) + 3 + (20 if with_tex else 0)
+    w0, w1 = torch.randn(K, D, generator=g) * 0.3, torch.randn(K, D, generator=g) * 0.3
+    res = torch.randn(SV, D, generator=g)
+    go = torch.randn(SV, D, generator=g)
+    return dict(v_index=v_index, adj=adj, SV=SV, pos=pos, feat=feat, fmap=fmap, w0=w0, w1=w1, res=res, go=go, B=B)
+
+
+@pytest.mark.parametrize("with_feat,with_tex,with_res", [(True, True, False), (False, True, True), (True, False, True),
+                                                         (False, False, False)])
+def test_graph_conv_parts_vs_oracle(lib, with_feat, with_tex, with_res):
+    """relu([feat | pos | aligned] W0 + A([..] W1)) (+ residual) evaluated from its parts: values and every gradient
+    (parts, feature map, weights, residual) against the fp64 oracle on the materialised concatenation."""
+    from meshrcnn_b200 import functional as F_
+    c = _parts_case(with_feat, with_tex)
+    sizes, mi = [(224, 224)] * c["B"], [1] * c["B"]
+
+    def oracle(dt):
+        pos = c["pos"].to(dt).requires_grad_()
+        feat = c["feat"].to(dt).requires_grad_() if with_feat else None
+        fmap = c["fmap"].to(dt).requires_grad_() if with_tex else None
+        w0, w1 = c["w0"].to(dt).requires_grad_(), c["w1"].to(dt).requires_grad_()
+        res = c["res"].to(dt).requires_grad_() if with_res else None
+        cols = ([feat] if with_feat else []) + [pos] + ([mesh_ops.vert_align([fmap], pos.detach(), c["v_index"], sizes, mi)] if with_tex else [])
+        out = mesh_ops.graph_conv(torch.cat(cols, 1), c["adj"].cpu(), w0, w1)
+        if with_res:
+            out = out + res
+        (out * c["go"].to(dt)).sum().backward()
+        return dict(out=out.detach(), pos=pos.grad, feat=None if feat is None else feat.grad, fmap=None if fmap is None else fmap.grad,
+                    w0=w0.grad, w1=w1.grad, res=None if res is None else res.grad)
+
+    want = oracle(torch.float64)
+    pos = c["pos"].cuda().requires_grad_()
+    feat = c["feat"].cuda().requires_grad_() if with_feat else None
+    fmap = c["fmap"].cuda().requires_grad_() if with_tex else None
+    w0, w1 = c["w0"].cuda().requires_grad_(), c["w1"].cuda().requires_grad_()
+    res = c["res"].cuda().requires_grad_() if with_res else None
+    parts = ([("x", feat)] if with_feat else []) + [("pos", pos)]
+    if with_tex:
+        tex = F_.TexelTerm(fmap, pos, c["v_index"], sizes, mi)
+        assert float((tex.texrow >= 0).float().mean()) > 0.5            # the gather is exercised
+        parts.append(("tex", tex))
+    out = F_.graph_conv_parts(parts, c["adj"], w0, w1, res)
+    (out * c["go"].cuda()).sum().backward()
+    got = dict(out=out, pos=pos.grad, feat=None if feat is None else feat.grad, fmap=None if fmap is None else fmap.grad,
+               w0=w0.grad, w1=w1.grad, res=None if res is None else res.grad)
+    for k, wv in want.items():
+        if wv is None:
+            continue
+        close(got[k], wv, what="parts %s" % k)
+
+
+def test_position_head_vs_oracle(lib):
+    """pos + tanh([pos | x] W^T) (Pix3D), pos + tanh(x W^T) (ShapeNet): one kernel forward, fused backward."""
+    from meshrcnn_b200 import functional as F_
+    g = torch.Generator().manual_seed(9)
+    n, Kx = 1001, 128
+    x, pos = torch.randn(n, Kx, generator=g) * 0.3, torch.randn(n, 3, generator=g)
+    go = torch.randn(n, 3, generator=g)
+    for pos_first in (True, None):
+        w = torch.randn(3, Kx + (3 if pos_first else 0), generator=g) * 0.1
+        xd, pd, wd = (t.double().requires_grad_() for t in (x, pos, w))
+        inp = torch.cat([pd, xd], 1) if pos_first else xd
+        want = pd + torch.tanh(inp @ wd.t())
+        (want * go.double()).sum().backward()
+        xc, pc, wc = (t.cuda().requires_grad_() for t in (x, pos, w))
+        got = F_.position_head(xc, pc, wc, pos_first)
+        (got * go.cuda()).sum().backward()
+        close(got, want.detach(), what="head out")
+        close(xc.grad, xd.grad, what="head gx")
+        close(pc.grad, pd.grad, what="head gpos")
+        close(wc.grad, wd.grad, what="head gW")
+
+
+@pytest.mark.parametrize("model", ["pix3d", "shapenet", "shapenet_residual"])
+def test_fused_stages_equal_literal_stages(lib, model):
+    """FUSE_STAGE_INPUTS (parts, texel gather, fused head, residual epilogue) against the literal evaluation (concatenate,
+    generic kernels) of the same stage chain: outputs and all parameter / map gradients at rtol 1e-4 (relative L2)."""
+    import meshrcnn_b200.layers as L
+    from meshrcnn_b200 import synthetic
+    from meshrcnn_b200.pipeline import RefinementHead
+    B, V = 2, 10
+    vox = synthetic.blob_voxels(B, V, 3)
+    torch.manual_seed(2)
+    head = RefinementHead(model, cubify_threshold=0.2).cuda().eval()
+    with torch.no_grad():
+        for prm in head.parameters():
+            prm.mul_(0.2)
+    img = 224 if model == "pix3d" else 137
+    maps = [synthetic.PIX3D_MAP] if model == "pix3d" else synthetic.SHAPENET_MAPS
+    fmaps = [m * 0.05 for m in synthetic.feature_maps(B, maps, 1)]
+    verts, v_index, faces, f_index, adj = head.cubify(vox.cuda())
+    SV = verts.shape[0]
+    pos0 = synthetic.in_frustum_positions(SV, img, 9)
+    sizes = [(img, img)] * B
+    go = torch.randn(SV, 3, generator=torch.Generator().manual_seed(4)).cuda()
+    gf = torch.randn(SV, 128, generator=torch.Generator().manual_seed(5)).cuda()
+
+    def run(fused):
+        L.FUSE_STAGE_INPUTS = fused
+        try:
+            head.zero_grad(set_to_none=True)
+            fm = [m.cuda().requires_grad_() for m in fmaps]
+            p = pos0.cuda().requires_grad_()
+            cur, feats = p, None
+            for st in head.refineStages:
+                cur, feats = st(v_index, fm[0] if model == "pix3d" else fm, adj, cur, sizes, vertex_features=feats)
+            ((cur * go).sum() + (feats * gf).sum()).backward()
+            out = {"pos": cur.detach(), "feat": feats.detach(), "g pos0": p.grad}
+            for i, m in enumerate(fm):
+                out["g fmap%d" % i] = m.grad
+            for k, prm in head.named_parameters():
+                out["g " + k] = prm.grad.clone()
+            return out
+        finally:
+            L.FUSE_STAGE_INPUTS = True
+
+    a, b = run(True), run(False)
+    assert a.keys() == b.keys()
+    for k in a:
+        w = b[k].double()
+        err = float((a[k].double() - w).norm() / max(float(w.norm()), 1e-30))
+        assert err <= 1e-4, (k, err)

@@ -251,3 +251,29 @@ def test_batched_mesh_loss_runs_and_is_finite(lib):
         assert t.dim() == 0 and bool(torch.isfinite(t))
     for p in pos:
         assert bool(torch.isfinite(p.grad).all()) and float(p.grad.abs().sum()) > 0
+
+
+def test_gt_sampling_cdf_cache(lib):
+    """the area CDF of the static GT meshes is computed once per batch object; sampling through the cache is
+    bit-identical to sampling without it, and an in-place edit of the vertices invalidates the cache."""
+    from meshrcnn_b200 import _lib, functional as F_, synthetic
+    from meshrcnn_b200.layers import Cubify
+    B = 3
+    verts, vi, faces, fi, _ = Cubify(0.5)(synthetic.blob_voxels(B, 12, 1000).cuda())
+    verts = verts * 0.05
+    owner = FakeBatch((verts, faces), vi, fi)
+    plain, f0 = F_.sample_points(verts, faces, vi, fi, 500, seed=7)
+    n0 = _lib.launch_count
+    c1, f1 = F_.sample_points(verts, faces, vi, fi, 500, seed=7, cdf_owner=owner)
+    first = _lib.launch_count - n0
+    n0 = _lib.launch_count
+    c2, f2 = F_.sample_points(verts, faces, vi, fi, 500, seed=7, cdf_owner=owner)
+    second = _lib.launch_count - n0
+    assert torch.equal(plain, c1) and torch.equal(c1, c2) and torch.equal(f0, f1) and torch.equal(f1, f2)
+    assert second == first - _lib.LAUNCHES["mrb_face_area_cdf"]            # the CDF kernels ran only once
+    key = owner._mrb_face_cdf[0]
+    verts[: vi[0]] *= 2.0                                                   # in-place edit -> new version -> recomputed
+    c3, _ = F_.sample_points(verts, faces, vi, fi, 500, seed=7, cdf_owner=owner)
+    assert owner._mrb_face_cdf[0] != key
+    want, _ = F_.sample_points(verts, faces, vi, fi, 500, seed=7)
+    assert torch.equal(c3, want)
