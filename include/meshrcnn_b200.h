@@ -39,7 +39,8 @@ long long mrb_fma_peak(float* out, int iters, int blocks, void* stream);
  *
  * Two phases because output sizes are data dependent and the module API returns Python lists
  * (layers.py:445,448,484):
- *   1. mrb_cubify_count  : threshold (strict >, fp32), exposed-face flags, per-block counts, scans.
+ *   1. mrb_cubify_count  : threshold (strict >, fp32; from_logits != 0: the grid holds the voxel head's logits and
+ *        sigmoid(logit) > threshold is tested), exposed-face flags, per-block counts, scans.
  *        meta (int64, 4 + 4*B entries): [0]=total vertices, [1]=total faces, [2]=directed edges E, [3]=0,
  *        then v_count[B], f_count[B], v_offset[B], f_offset[B].
  *   2. (caller copies meta to the host -- the only synchronisation -- and allocates the outputs)
@@ -51,11 +52,22 @@ long long mrb_fma_peak(float* out, int iters, int blocks, void* stream);
  * An all-empty batch yields meta[1] == 0; the Python layer raises ValueError("empty grid") like layers.py:434-435.
  */
 long long mrb_cubify_workspace_bytes(int B, int Z, int Y, int X);
-int mrb_cubify_count(const float* probs, int B, int Z, int Y, int X, float threshold, void* workspace,
+int mrb_cubify_count(const float* probs, int B, int Z, int Y, int X, float threshold, int from_logits, void* workspace,
                      long long* meta, void* stream);
 int mrb_cubify_emit(int B, int Z, int Y, int X, void* workspace, const long long* meta, long long SV, long long SF,
                     long long E, float* verts, long long* faces, long long* adj, int32_t* rowptr, int32_t* col32,
                     int32_t* vert_mesh, void* vert_aux, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Voxel-head tail -- replaces nn.Sigmoid at the end of VoxelBranch (meshRCNN/layers.py:487-506) + voxel_loss
+ * (meshRCNN/loss_functions.py:10-14) as one pass over the logits: loss_out[0] = mean BCE(sigmoid(x), target) with torch's
+ * clamp of the log terms at -100 (from_logits != 0; probs_out, optional, receives the probabilities) or
+ * mean BCE(x, target) on probabilities (from_logits == 0).  acc: 1 double of scratch.  Backward: gx = *g / n * dBCE/dx.
+ */
+int mrb_voxel_bce_fwd(const float* x, const float* target, long long n, int from_logits, float* probs_out, double* acc,
+                      float* loss_out, void* stream);
+int mrb_voxel_bce_bwd(const float* x, const float* target, long long n, int from_logits, const float* g, float* gx,
+                      void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Graph utilities.

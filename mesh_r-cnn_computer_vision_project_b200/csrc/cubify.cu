@@ -92,20 +92,28 @@ static size_t carve(const Dims& d, void* base, Workspace* ws) {
 // ---------------------------------------------------------------------------------------------------------
 // pass 1a: threshold + exposed-face flags + per-(mesh, dir, chunk) face counts
 // ---------------------------------------------------------------------------------------------------------
+// occupancy test: probs > th (strict, fp32 -- layers.py:405), or sigmoid(logit) > th when the grid holds the voxel head's
+// logits (the sigmoid of VoxelBranch folded into Cubify; same formula as voxel.cu / torch's CUDA sigmoid)
+template <bool LOGITS>
+__device__ __forceinline__ bool occupied(float v, float th) {
+    return (LOGITS ? 1.0f / (1.0f + expf(-v)) : v) > th;
+}
+
+template <bool LOGITS>
 __global__ void __launch_bounds__(CH) k_faceflags(const float* __restrict__ probs, float th, Dims d, Workspace ws) {
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int v = chunk * CH + threadIdx.x;
     unsigned f = 0;
     if (v < d.nvox) {
         const float* p = probs + (size_t)b * d.nvox;
-        if (__ldg(p + v) > th) {                       // strict '>' in fp32 (layers.py:405)
+        if (occupied<LOGITS>(__ldg(p + v), th)) {
             const int x = v % d.X, y = (v / d.X) % d.Y, z = v / (d.X * d.Y);
 #pragma unroll
             for (int k = 0; k < 6; ++k) {
                 const int nz = z + kNbr[k][0], ny = y + kNbr[k][1], nx = x + kNbr[k][2];
                 bool occ = false;                      // zero padding (layers.py:411)
                 if (nz >= 0 && nz < d.Z && ny >= 0 && ny < d.Y && nx >= 0 && nx < d.X)
-                    occ = __ldg(p + ((size_t)nz * d.Y + ny) * d.X + nx) > th;
+                    occ = occupied<LOGITS>(__ldg(p + ((size_t)nz * d.Y + ny) * d.X + nx), th);
                 if (!occ) f |= 1u << k;
             }
         }
@@ -331,8 +339,8 @@ extern "C" long long mrb_cubify_workspace_bytes(int B, int Z, int Y, int X) {
     return (long long)carve(d, nullptr, nullptr);
 }
 
-extern "C" int mrb_cubify_count(const float* probs, int B, int Z, int Y, int X, float threshold, void* workspace,
-                                long long* meta, void* stream_) {
+extern "C" int mrb_cubify_count(const float* probs, int B, int Z, int Y, int X, float threshold, int from_logits,
+                                void* workspace, long long* meta, void* stream_) {
     MRB_REQUIRE(probs && workspace && meta, "cubify_count: null pointer");
     MRB_REQUIRE(B > 0 && Z > 0 && Y > 0 && X > 0, "cubify_count: bad grid %dx%dx%dx%d", B, Z, Y, X);
     MRB_REQUIRE((long long)B * (Z + 1) * (Y + 1) * (X + 1) < (1LL << 31), "cubify_count: lattice too large for int32");
@@ -341,7 +349,8 @@ extern "C" int mrb_cubify_count(const float* probs, int B, int Z, int Y, int X, 
     Dims d = make_dims(B, Z, Y, X);
     Workspace ws;
     carve(d, workspace, &ws);
-    k_faceflags<<<dim3(d.nchF, B), CH, 0, stream>>>(probs, threshold, d, ws);
+    if (from_logits) k_faceflags<true><<<dim3(d.nchF, B), CH, 0, stream>>>(probs, threshold, d, ws);
+    else k_faceflags<false><<<dim3(d.nchF, B), CH, 0, stream>>>(probs, threshold, d, ws);
     k_lattice_count<<<dim3(d.nchL, B), CH, 0, stream>>>(d, ws);
     k_scan<<<3, 1024, 0, stream>>>(d, ws, meta);
     return check_launch("cubify_count");

@@ -134,6 +134,10 @@ constexpr int EPI_WARPS = 8;         // epilogue warps: TMEM lane quadrant = war
 constexpr int TC_THREADS = (PROD_WARPS + EPI_WARPS + 2) * 32;   // producers | epilogue warps | MMA issuer | weight TMA
 constexpr int EPI_BYTES = EPI_WARPS * 32 * 33 * 4;
 constexpr int TC_MAX_STAGES = 4;
+#ifndef MRB_TC_SINGLE_ACC_CHUNKS
+#define MRB_TC_SINGLE_ACC_CHUNKS 16
+#endif
+constexpr int TC_SINGLE_ACC_CHUNKS = MRB_TC_SINGLE_ACC_CHUNKS;   // K <= 512: one TMEM accumulator for all three 3xTF32 products
 constexpr int TC_SMEM_LIMIT = 232448;                                    // 227 KB opt-in maximum per CTA
 constexpr int TC_RING_BYTES = TC_SMEM_LIMIT - EPI_BYTES - 1024 - 256;   // what the stage ring may use
 
@@ -322,10 +326,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
                     uint32_t v0[32], v1[32];
                     const uint32_t taddr = tmem_d + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0;
                     tmem_ld32(taddr, v0);
-                    tmem_ld32(taddr + (uint32_t)p.tmem_cols, v1);         // nacc >= 2 always (main + cross-term accumulator)
+                    if (p.nacc > 1) tmem_ld32(taddr + (uint32_t)p.tmem_cols, v1);   // main + cross-term accumulator
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (p.nacc > 1) {
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) acc[q] = __uint_as_float(v0[q]) + __uint_as_float(v1[q]);
+                        for (int q = 0; q < 32; ++q) acc[q] = __uint_as_float(v0[q]) + __uint_as_float(v1[q]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) acc[q] = __uint_as_float(v0[q]);
+                    }
                     for (int a = 2; a < p.nacc; ++a) {
                         tmem_ld32(taddr + (uint32_t)(a * p.tmem_cols), v1);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -417,13 +426,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
                         // The fp32 accumulate of the tensor core truncates (error ~1 ulp of the accumulator per MMA, biased), so
                         // the two small cross terms get their own accumulator (2^-11 of the magnitude: their truncation is
                         // negligible) and only the K/8 hi*hi products are chained into the main one(s).
-                        const int nmain = p.nacc - 1;
+                        // (short reductions -- nacc == 1 -- chain all three products into one accumulator, like the weight-
+                        // gradient kernel does for <= 384 MMAs: that leaves room for a second accumulator set, so the epilogue of
+                        // a 256-column tile overlaps the next tile's MMAs)
+                        const int nmain = max(p.nacc - 1, 1);
                         const uint32_t d_main = tmem_d + (uint32_t)((c % nmain) * p.tmem_cols);
-                        const uint32_t d_aux = tmem_d + (uint32_t)(nmain * p.tmem_cols);
+                        const uint32_t d_aux = p.nacc > 1 ? tmem_d + (uint32_t)(nmain * p.tmem_cols) : d_main;
 #ifndef MRB_DIAG_NOMMA
                         umma_tf32(d_aux, dal, dbh, idesc, (c | kk) != 0);
                         umma_tf32(d_aux, dah, dbl, idesc, 1);
-                        umma_tf32(d_main, dah, dbh, idesc, (c >= nmain) || kk != 0);
+                        umma_tf32(d_main, dah, dbh, idesc, p.nacc > 1 ? ((c >= nmain) || kk != 0) : 1);
 #endif
                     }
                     umma_commit(empty_bar(s));                 // stage reusable once these MMAs retire
@@ -824,6 +836,11 @@ static int launch_gemm_tc(const float* A, int lda, int M, int K, const void* ima
         // accumulators: one for the lo cross terms + 1 or 3 main ones (long segments, when TMEM allows); power of two
         p.nacc = 2;
         if (nch > 16 && 4 * pl.tmem_cols <= 512) p.nacc = 4;
+        // 256-column tiles: main + cross-term accumulators fill the 512 TMEM columns, so the tensor pipe would idle during
+        // every epilogue.  For reductions of <= TC_SINGLE_ACC_CHUNKS chunks (<= 192 chained MMAs; the weight-gradient kernel
+        // chains 384) one accumulator is accurate enough (measured rel. L2 error vs fp64 in tests/test_gemm_gpu.py) and the
+        // accumulator can be double buffered.
+        if (2 * p.nacc * pl.tmem_cols > 512 && nch <= TC_SINGLE_ACC_CHUNKS) p.nacc = 1;
         p.acc_bufs = (2 * p.nacc * pl.tmem_cols <= 512) ? 2 : 1;
         p.mtiles = ceil_div(M, BM);
         p.ntiles = pl.ntiles;
@@ -866,9 +883,13 @@ static int launch_wgrad(const float* X, int ldx, const float* G, int ldg, int V,
     p.ldc = ldc; p.tail = n_tail; p.Xtail = Xtail; p.ld_tail = ld_tail; p.T0 = T0; p.T1 = T1;
     const int mtiles = ceil_div(Kin, BM);
     const int total_chunks = ceil_div(V, BK);
-    int splits = max(1, min(total_chunks, kNumSMs / mtiles));
-    p.chunks_per_split = min(ceil_div(total_chunks, splits), 32);    // <= 384 MMAs chained per accumulator (truncating adds)
-    splits = ceil_div(total_chunks, p.chunks_per_split);
+    // <= 32 chunks (384 chained, truncating MMAs) per CTA, and a CTA count that fills whole waves of the 148 SMs: with the cap
+    // alone, V = 206k gave 202 CTAs = 1.36 waves (a third of the machine idle during the second one)
+    const int per_wave = max(1, kNumSMs / mtiles);
+    int waves = 1;
+    while (ceil_div(total_chunks, per_wave * waves) > 32) ++waves;
+    p.chunks_per_split = max(1, ceil_div(total_chunks, per_wave * waves));
+    const int splits = ceil_div(total_chunks, p.chunks_per_split);
     if (N <= 128) k_gemm_tn<4, 2><<<dim3(mtiles, splits), TN_THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(p);
     else k_gemm_tn<8, 1><<<dim3(mtiles, splits), TN_THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(p);
     return check_launch(what);

@@ -1,7 +1,10 @@
-"""Eval-side helpers next to the hot path: the metrics of the reference ``utils/metrics.py`` and the
-detection-selection + adjacency rebuild of ``utils/eval_utils.py:12-90``.  Device-agnostic tensor code (works on the
-GPU tensors the refinement head returns in eval mode and on CPU tensors); no custom kernels are involved: the rebuilt
-adjacency is handed to the CSR path through ``topology.from_coo`` like any foreign COO tensor.
+"""Eval-side helpers next to the hot path: the metrics of the reference ``utils/metrics.py``, the
+detection-selection + adjacency rebuild of ``utils/eval_utils.py:12-90``, and the device path of ``validate``
+(``utils/eval_utils.py:93-194``): ``validate_batch`` evaluates the voxel / chamfer / normal / edge losses of an eval-mode
+output dict over all its position sets through the CUDA kernels and adds the geometric F1@tau of the final meshes from
+the nearest-neighbour distances the k-NN kernel already returns; ``validate`` averages it over a loader with the
+reference's metric names.  The metric helpers are device-agnostic tensor code; the rebuilt adjacency is handed to the CSR
+path through ``topology.from_coo`` like any foreign COO tensor.
 
 Reference semantics kept: ``f_score`` works on a confusion matrix c[i, j] = #(predicted i, ground truth j) and returns
 percentages with the 1e-8 guards of :20-26; ``mesh_precision_recall`` zeroes ALL true positives through the scalar-mask
@@ -109,3 +112,72 @@ def get_only_max(max_indexes: Sequence[int], voxels: Tensor, vertex_positions: L
         run += n
     adj = faces_to_adjacency(torch.cat([f + off for f, off in zip(res_fs, offsets)]))
     return vxls, res_vs, torch.cat(res_fs), adj, res_v_index, res_f_index
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# validate on the device path (reference utils/eval_utils.py:93-194)
+# ---------------------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def validate_batch(model_output: dict, batch, point_cloud_size: float = 10e3, num_neighbours_for_normal_loss: int = 10,
+                   f1_thresholds: Sequence[float] = (0.1, 0.3, 0.5), randomness=None, f1_seed: int = 0) -> dict:
+    """Losses of one eval-mode output dict (keys ``vertex_positions`` (list, incl. the cubified stage-0 set), ``faces``,
+    ``edge_index``, ``vertice_index``, ``face_index``; optional ``voxels``) against ``batch`` (``.meshes``,
+    ``.vertice_index``, ``.face_index``, optional ``.voxels``) -- what reference ``validate`` computes per batch
+    (eval_utils.py:160-164: ``voxel_loss`` + ``batched_mesh_loss`` over ALL position sets), on the CUDA kernels.
+
+    Added: ``f1@tau`` of the final meshes -- precision = share of predicted surface samples within ``tau`` of
+    the ground-truth samples, recall the converse, F1 = 2PR / (P + R) in percent, averaged over the meshes; it costs one
+    extra nearest-neighbour call (k = 0) on 10 000-point clouds of the normalised meshes."""
+    from . import functional as F_
+    from .loss_functions import batched_mesh_loss, voxel_loss
+    vs, fs, e_index = model_output["vertex_positions"], model_output["faces"], model_output["edge_index"]
+    v_index, f_index = model_output["vertice_index"], model_output["face_index"]
+    out = {}
+    if model_output.get("voxels") is not None and getattr(batch, "voxels", None) is not None:
+        out["voxel_loss"] = voxel_loss(model_output["voxels"], batch.voxels)
+    chamfer, normal, edge = batched_mesh_loss(list(vs), fs, e_index, v_index, f_index, batch, point_cloud_size,
+                                              num_neighbours_for_normal_loss, randomness=randomness)
+    out.update({"chamfer_loss": chamfer, "normal_loss": normal, "edge_loss": edge})
+    n = int(point_cloud_size)
+    gt_pos, gt_faces = batch.meshes
+    cloud_p, _ = F_.sample_points(vs[-1], fs, v_index, f_index, n, seed=f1_seed)
+    cloud_g, _ = F_.sample_points(gt_pos, gt_faces, batch.vertice_index, batch.face_index, n, seed=f1_seed + 1, cdf_owner=batch)
+    d_p, _, _, d_g, _, _ = F_.knn_search(cloud_p, cloud_g, 0)
+    d_p, d_g = d_p.sqrt(), d_g.sqrt()
+    for tau in f1_thresholds:
+        prec = (d_p < tau).float().mean(dim=1)
+        rec = (d_g < tau).float().mean(dim=1)
+        out["f1@%g" % tau] = (100.0 * 2 * prec * rec / (prec + rec).clamp_min(1e-8)).mean()
+    return out
+
+
+class AverageMeter:
+    """Running average with the reference's interface (utils/train_utils.py AverageMeter: ``update(val, n)``, ``.avg``)."""
+
+    def __init__(self, name: str):
+        self.name, self.sum, self.count, self.val = name, 0.0, 0, 0.0
+
+    def update(self, val: float, n: int = 1) -> None:
+        self.val = float(val)
+        self.sum += float(val) * n
+        self.count += n
+
+    @property
+    def avg(self) -> float:
+        return self.sum / max(self.count, 1)
+
+
+def validate(model, val_loader, device=None, point_cloud_size: float = 10e3, num_neighbours_for_normal_loss: int = 10) -> dict:
+    """Mesh-side validation loop (reference ``validate``, eval_utils.py:93-194, without the backbone / classification
+    metrics that are outside the hot path): ``model(images)`` must return the eval-mode output dict; returns AverageMeters
+    named like the reference's (``voxel_loss``, ``chamfer_loss``, ``normal_loss``, ``edge_loss``) plus ``f1@tau``."""
+    model.eval()
+    meters = {}
+    for batch in val_loader:
+        if device is not None:
+            batch = batch.to(device, non_blocking=True)
+        res = validate_batch(model(batch.images), batch, point_cloud_size, num_neighbours_for_normal_loss)
+        n = len(batch.vertice_index)
+        for k, v in res.items():
+            meters.setdefault(k, AverageMeter(k)).update(float(v), n)
+    return meters

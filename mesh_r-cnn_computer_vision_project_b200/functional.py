@@ -36,8 +36,9 @@ def _require_cuda(t: Tensor, what: str) -> None:
 # Cubify
 # ----------------------------------------------------------------------------------------------------------
 @torch.no_grad()
-def cubify(t: Tensor, threshold: float):
-    """See ``layers.Cubify``.  Returns (verts, v_index, faces, f_index, adj, topology)."""
+def cubify(t: Tensor, threshold: float, from_logits: bool = False):
+    """See ``layers.Cubify``.  Returns (verts, v_index, faces, f_index, adj, topology).  ``from_logits``: ``t`` holds the
+    voxel head's logits and ``sigmoid(t) > threshold`` is tested inside the first kernel."""
     _require_cuda(t, "Cubify")
     if t.dim() != 4:
         raise RuntimeError("Cubify expects B x Z x Y x X, got %s" % (tuple(t.shape),))
@@ -51,7 +52,8 @@ def cubify(t: Tensor, threshold: float):
             raise RuntimeError("Cubify: bad grid shape %s" % (tuple(t.shape),))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         meta = torch.empty(4 + 4 * B, dtype=torch.int64, device=dev)
-        _lib.call("mrb_cubify_count", _lib.ptr(probs), B, Z, Y, X, float(threshold), _lib.ptr(ws), _lib.ptr(meta))
+        _lib.call("mrb_cubify_count", _lib.ptr(probs), B, Z, Y, X, float(threshold), int(bool(from_logits)), _lib.ptr(ws),
+                  _lib.ptr(meta))
         meta_h = meta.cpu()                      # the one unavoidable sync: the API returns Python lists
         SV, SF, E = int(meta_h[0]), int(meta_h[1]), int(meta_h[2])
         if SF == 0:
@@ -72,6 +74,42 @@ def cubify(t: Tensor, threshold: float):
     topo = MeshTopology(SV, E, rowptr, col32, symmetric=True, vert_mesh=vert_mesh)
     register(adj, topo)
     return verts, v_counts[:last], faces, f_counts[:last], adj, topo
+
+
+class _VoxelBCE(torch.autograd.Function):
+    """mean BCE on probabilities (reference voxel_loss, loss_functions.py:10-14) or on logits with the sigmoid fused."""
+
+    @staticmethod
+    def forward(ctx, x, target, from_logits, want_probs):
+        _require_cuda(x, "voxel_loss")
+        xc = _f32c(x)
+        tc = _f32c(target)
+        if xc.shape != tc.shape:
+            raise RuntimeError("voxel_loss: prediction %s and target %s differ in shape" % (tuple(xc.shape), tuple(tc.shape)))
+        dev = x.device
+        probs = torch.empty_like(xc) if (from_logits and want_probs) else None
+        acc = torch.empty(1, dtype=torch.float64, device=dev)
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        _lib.call("mrb_voxel_bce_fwd", _lib.ptr(xc), _lib.ptr(tc), xc.numel(), int(from_logits), _lib.ptr(probs), _lib.ptr(acc),
+                  _lib.ptr(out))
+        ctx.save_for_backward(xc, tc)
+        ctx.from_logits = bool(from_logits)
+        if probs is not None:
+            ctx.mark_non_differentiable(probs)
+        return out[0], probs
+
+    @staticmethod
+    def backward(ctx, g, _gprobs):
+        xc, tc = ctx.saved_tensors
+        gx = torch.empty_like(xc)
+        _lib.call("mrb_voxel_bce_bwd", _lib.ptr(xc), _lib.ptr(tc), xc.numel(), int(ctx.from_logits), _lib.ptr(_f32c(g).reshape(1)),
+                  _lib.ptr(gx))
+        return gx, None, None, None
+
+
+def voxel_bce(x: Tensor, target: Tensor, from_logits: bool = False, want_probs: bool = False):
+    """(loss, probs | None): mean binary cross entropy of the voxel head -- one pass over ``x`` (fp64 accumulation)."""
+    return _VoxelBCE.apply(x, target, from_logits, want_probs)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -300,6 +338,7 @@ class _GraphConv(torch.autograd.Function):
         y = torch.empty(n, 2 * D, dtype=torch.float32, device=x.device)
         yp = _lib.ptr(y)
         ctx.img_bwd = None
+        ctx.wcat = None
         if _use_tc(K, 2 * D):      # one tensor-core pass over x for [x W0 | x W1]
             if ctx.needs_input_grad[0] and _use_tc(2 * D, K):
                 # the operand image of the input gradient is packed by the same launch (the weights cannot change between
@@ -311,9 +350,9 @@ class _GraphConv(torch.autograd.Function):
             else:
                 img = tc_pack(w0, w1, D, 1, 1, D, K, 2 * D)
             tc_gemm(xp, ldx, n, K, img, 2 * D, yp, 2 * D)
-        else:
-            _gemm(False, False, n, D, K, xp, ldx, _lib.ptr(w0), D, 0.0, yp, 2 * D)
-            _gemm(False, False, n, D, K, xp, ldx, _lib.ptr(w1), D, 0.0, yp + 4 * D, 2 * D)
+        else:                      # narrow layers (the 3-wide ShapeNet head): one CUDA-core pass over x for [x W0 | x W1]
+            ctx.wcat = torch.cat([w0, w1], 1)
+            _gemm(False, False, n, 2 * D, K, xp, ldx, _lib.ptr(ctx.wcat), 2 * D, 0.0, yp, 2 * D)
         out = torch.empty(n, D, dtype=torch.float32, device=x.device)
         _gather(topo.rowptr, topo.col, n, yp, 2 * D, yp + 4 * D, 2 * D, D, True, _lib.ptr(out), D)
         ctx.save_for_backward(x, w0, w1, out)
@@ -347,20 +386,19 @@ class _GraphConv(torch.autograd.Function):
                 img = ctx.img_bwd if ctx.img_bwd is not None else tc_pack(w0, w1, 1, D, 2, D, 2 * D, K)
                 tc_gemm(gp, 2 * D, n, 2 * D, img, K, gxp, ldgx)
             else:
-                _gemm(False, True, n, K, D, gp, 2 * D, _lib.ptr(w0), D, 0.0, gxp, ldgx)
-                _gemm(False, True, n, K, D, gp + 4 * D, 2 * D, _lib.ptr(w1), D, 1.0, gxp, ldgx)
+                wcat = getattr(ctx, "wcat", None)
+                if wcat is None:
+                    wcat = torch.cat([w0, w1], 1)
+                _gemm(False, True, n, K, 2 * D, gp, 2 * D, _lib.ptr(wcat), 2 * D, 0.0, gxp, ldgx)
         if (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) and _use_tc_wgrad(n, 2 * D) and D % 32 == 0:
             # dW0 | dW1 = x^T @ [gz | A^T gz]: one tensor-core pass over x and gy, reduced over the vertices
             gw = torch.zeros(2, K, D, dtype=torch.float32, device=x.device)
             _lib.call("mrb_gemm_tc_wgrad", xp, ldx, gp, 2 * D, n, K, 2 * D, _lib.ptr(gw), _lib.ptr(gw) + 4 * K * D, D, D)
             gw0, gw1 = gw[0], gw[1]
-        else:
-            if ctx.needs_input_grad[1]:
-                gw0 = torch.empty_like(w0)
-                _gemm(True, False, K, D, n, xp, ldx, gp, 2 * D, 0.0, _lib.ptr(gw0), D)
-            if ctx.needs_input_grad[2]:
-                gw1 = torch.empty_like(w1)
-                _gemm(True, False, K, D, n, xp, ldx, gp + 4 * D, 2 * D, 0.0, _lib.ptr(gw1), D)
+        elif ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            gwcat = torch.empty(K, 2 * D, dtype=torch.float32, device=x.device)      # [dW0 | dW1] = x^T gy in one pass
+            _gemm(True, False, K, 2 * D, n, xp, ldx, gp, 2 * D, 0.0, _lib.ptr(gwcat), 2 * D)
+            gw0, gw1 = gwcat[:, :D], gwcat[:, D:]
         return gx, gw0, gw1, None
 
 

@@ -47,9 +47,31 @@ class Cubify(nn.Module):
         self.register_buffer("kernel", kernel)
         self.register_buffer("deltas", deltas)
 
-    def forward(self, t: Tensor):
-        verts, v_index, faces, f_index, adj, _ = F_.cubify(t, float(self.threshold))
+    def forward(self, t: Tensor, from_logits: bool = False):
+        """``from_logits=True`` (extension): ``t`` holds the voxel head's logits; ``sigmoid(t) > threshold`` is
+        evaluated inside the first kernel, so the probability grid is never written."""
+        verts, v_index, faces, f_index, adj, _ = F_.cubify(t, float(self.threshold), from_logits)
         return verts, v_index, faces, f_index, adj
+
+
+class VoxelBranch(nn.Sequential):
+    """Voxel occupancy head -- reference meshRCNN/layers.py:487-506, same modules and state-dict keys (``0.weight`` ...
+    ``3.bias``; the convolutions are library calls and outside the hot path).  ``forward`` returns probabilities like the
+    reference; ``forward_logits`` stops before the final ``nn.Sigmoid`` so that its two consumers -- ``voxel_loss_with_logits``
+    and ``Cubify(..)(logits, from_logits=True)`` -- evaluate the sigmoid inside their own first pass."""
+
+    def __init__(self, in_channels: int, out_channels: int, hidden_channels: int = 256):
+        super().__init__(
+            nn.Conv2d(in_channels, hidden_channels, kernel_size=3, padding=1),
+            nn.Conv2d(hidden_channels, hidden_channels, kernel_size=3, padding=1),
+            nn.ConvTranspose2d(hidden_channels, hidden_channels, kernel_size=2, stride=2),
+            nn.Conv2d(hidden_channels, out_channels, kernel_size=1),
+            nn.Sigmoid())
+
+    def forward_logits(self, x: Tensor) -> Tensor:
+        for m in list(self)[:-1]:
+            x = m(x)
+        return x
 
 
 class VertexAlign(nn.Module):

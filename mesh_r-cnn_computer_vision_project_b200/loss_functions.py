@@ -9,16 +9,24 @@ thin compatibility functions for callers / tests that hold a distance matrix; ``
 from typing import List, Optional, Tuple
 
 import torch
-import torch.nn as nn
 from torch import Tensor
 
 from . import functional as F_
 
 
 def voxel_loss(voxel_prediction: Tensor, voxel_gts: Tensor) -> Tensor:
-    """BCE(mean) on the voxel probabilities -- reference loss_functions.py:10-14 (upstream of the hot path:
-    one library call, kept for API completeness)."""
-    return nn.functional.binary_cross_entropy(voxel_prediction, voxel_gts.float(), reduction='mean')
+    """mean BCE on the voxel occupancy probabilities -- reference loss_functions.py:10-14, one fused pass with fp64
+    accumulation and torch's clamp of the log terms (csrc/voxel.cu)."""
+    return F_.voxel_bce(voxel_prediction, voxel_gts, from_logits=False)[0]
+
+
+def voxel_loss_with_logits(voxel_logits: Tensor, voxel_gts: Tensor, return_probs: bool = False):
+    """The same loss taken from the voxel head's LOGITS: the ``nn.Sigmoid`` that ends the reference's
+    ``VoxelBranch`` (layers.py:505) is evaluated inside the loss kernel, so training never materialises the probability grid
+    (``Cubify(threshold)(logits, from_logits=True)`` thresholds the same sigmoid in its first kernel).  Returns the loss, or
+    ``(loss, probabilities)`` with ``return_probs=True`` (eval output dict, shapenet_model.py:66)."""
+    loss, probs = F_.voxel_bce(voxel_logits, voxel_gts, from_logits=True, want_probs=return_probs)
+    return (loss, probs) if return_probs else loss
 
 
 def batched_mesh_loss(vertex_positions_pred: List[Tensor], mesh_faces_pred: Tensor, pred_adjacency: Tensor,

@@ -60,11 +60,13 @@ class RefinementHead(nn.Module):
 
     def forward(self, voxel_probs: Tensor, feature_maps: Union[Tensor, List[Tensor]], image_sizes,
                 targets: Optional[MeshTargets] = None, mesh_index: Optional[List[int]] = None,
-                loss_randomness=None) -> dict:
+                loss_randomness=None, voxel_logits: bool = False) -> dict:
+        """``voxel_logits=True``: ``voxel_probs`` holds the voxel head's logits (``VoxelBranch.forward_logits``); the sigmoid
+        is evaluated inside Cubify's first kernel."""
         if self.training and targets is None:
             raise ValueError("In training mode, targets should be passed")
         mesh_index = [1 for _ in image_sizes] if mesh_index is None else mesh_index
-        pos0, vertice_index, faces, face_index, adj_index = self.cubify(voxel_probs)
+        pos0, vertice_index, faces, face_index, adj_index = self.cubify(voxel_probs, from_logits=voxel_logits)
         positions = [pos0]
         feats = None
         overlap = self.training and self.overlap_losses and voxel_probs.is_cuda

@@ -20,7 +20,7 @@ kp = torch.empty(B, P, max(k, 1), dtype=torch.int32, device=dev)
 dq = torch.empty(B, P, device=dev); iq = torch.empty(B, P, dtype=torch.int32, device=dev)
 kq = torch.empty(B, P, max(k, 1), dtype=torch.int32, device=dev)
 ws = torch.empty(_lib.load().mrb_knn_workspace_bytes(B, P, P), dtype=torch.uint8, device=dev)
-algo = int(sys.argv[2]) if len(sys.argv) > 2 else 0        # 0 auto, 1 tiled scan, 2 cell grid
+algo = int(sys.argv[2]) if len(sys.argv) > 2 else 0        # 0 auto, 1 tiled scan, 2 cell grid (warp per query), 3 cell grid (thread per query)
 def run():
     _lib.call("mrb_knn_fwd_algo", _lib.ptr(p), _lib.ptr(q), B, P, P, k, _lib.ptr(dp), _lib.ptr(ip), _lib.ptr(kp),
               _lib.ptr(dq), _lib.ptr(iq), _lib.ptr(kq), _lib.ptr(ws), algo)

@@ -95,3 +95,55 @@ def test_stress_config4_properties(lib):
     assert np.array_equal(vs[:nv].cpu().numpy(), o[0]) and np.array_equal(f[:nf].cpu().numpy(), o[2])
     ne = o[4].shape[1]
     assert np.array_equal(adj[:, :ne].cpu().numpy(), o[4])
+
+
+def test_cubify_from_logits_and_fused_voxel_loss(lib):
+    """the sigmoid that ends the reference's VoxelBranch (layers.py:505) folded into its two consumers.
+    Cubify(th)(logits, from_logits=True) == Cubify(th)(sigmoid(logits)) bit for bit (oracle on the CPU probabilities), and
+    voxel_loss_with_logits == BCE(sigmoid(logits)) of torch in fp64 (values rtol 1e-6, gradients rtol 1e-4); voxel_loss on
+    probabilities likewise (reference loss_functions.py:10-14)."""
+    import torch.nn.functional as TF
+    from meshrcnn_b200 import loss_functions as LF
+    from meshrcnn_b200.layers import Cubify, VoxelBranch
+    g = torch.Generator().manual_seed(5)
+    B, V, th = 3, 16, 0.2
+    logits = torch.randn(B, V, V, V, generator=g) * 3.0
+    probs = torch.sigmoid(logits)
+    near = (probs - th).abs() < 1e-5                   # keep clear of the threshold: CPU / GPU expf may differ in the last ulp
+    logits[near] += 0.01
+    probs = torch.sigmoid(logits)
+    want = cubify_np.cubify(probs.numpy(), th)
+    got = Cubify(th)(logits.cuda(), from_logits=True)
+    assert got[1] == want[1] and got[3] == want[3]
+    for i in (0, 2, 4):
+        assert np.array_equal(got[i].cpu().numpy(), want[i])
+    gt = (torch.rand(B, V, V, V, generator=g) < 0.3).float()
+    # loss on logits
+    x = logits.cuda().requires_grad_()
+    loss, p_out = LF.voxel_loss_with_logits(x, gt.cuda(), return_probs=True)
+    loss.backward()
+    x64 = logits.double().requires_grad_()
+    ref = TF.binary_cross_entropy(torch.sigmoid(x64), gt.double(), reduction="mean")
+    ref.backward()
+    assert abs(float(loss) - float(ref)) <= 1e-6 * abs(float(ref))
+    assert torch.allclose(p_out.cpu(), probs, rtol=1e-6, atol=1e-7)
+    assert torch.allclose(x.grad.cpu().double(), x64.grad, rtol=1e-4, atol=1e-9)
+    # loss on probabilities (the reference signature), incl. saturated entries (log clamp at -100)
+    pr = probs.clone()
+    pr.view(-1)[:7] = torch.tensor([0.0, 1.0, 1e-30, 1 - 1e-7, 0.5, 0.0, 1.0])
+    gt.view(-1)[:7] = torch.tensor([1.0, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0])
+    pc = pr.cuda().requires_grad_()
+    l2 = LF.voxel_loss(pc, gt.cuda())
+    l2.backward()
+    p64 = pr.double().requires_grad_()
+    r2 = TF.binary_cross_entropy(p64.float(), gt, reduction="mean")
+    assert abs(float(l2) - float(r2)) <= 1e-5 * abs(float(r2))
+    r64 = TF.binary_cross_entropy(p64, gt.double(), reduction="mean")
+    r64.backward()
+    inner = (pr > 1e-6) & (pr < 1 - 1e-6)
+    assert torch.allclose(pc.grad.cpu().double()[inner], p64.grad[inner], rtol=1e-4, atol=1e-12)
+    # the module mirror keeps the reference's state-dict keys and splits off the final sigmoid
+    vb = VoxelBranch(8, V, 16).cuda()
+    assert list(vb.state_dict()) == ["0.weight", "0.bias", "1.weight", "1.bias", "2.weight", "2.bias", "3.weight", "3.bias"]
+    feat = torch.randn(2, 8, V // 2, V // 2, generator=g).cuda()
+    assert torch.allclose(torch.sigmoid(vb.forward_logits(feat)), vb(feat), rtol=1e-6, atol=1e-7)

@@ -36,7 +36,9 @@ def _check(M, K, N, lda_pad=0, ldc_pad=0, split=None, transposed_src=False, seed
     err = float((got - want).abs().max())
     assert err <= 1e-5 * scale, (M, K, N, err, scale)
     rel = float((got - want).norm() / want.norm())
-    assert rel <= 2e-6, (M, K, N, rel)          # 3xTF32 with a separate accumulator for the cross terms: ~6e-7 (IEEE fp32: ~3e-7)
+    # 3xTF32: ~6e-7 with a separate accumulator for the cross terms, up to ~2e-6 when short reductions (K <= 512) chain all
+    # three products into one TMEM accumulator (256-column tiles, so that the accumulator can be double buffered); IEEE fp32: ~3e-7
+    assert rel <= 4e-6, (M, K, N, rel)
     if ldc_pad:
         assert bool((c[:, N:] == -7.0).all())          # no write outside the N columns
 

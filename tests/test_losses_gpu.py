@@ -167,13 +167,14 @@ def test_knn_grid_equals_tiled_scan(lib, kind, B, P, Q, k):
     ordered k-NN lists incl. (distance, index) tie-breaking); the tiled scan is itself checked against the oracle."""
     from meshrcnn_b200 import functional as F_
     p, q = _knn_clouds(kind, B, P, Q, seed=P + Q + k)
-    got = F_.knn_search(p.cuda(), q.cuda(), k, algo="grid")
     want = F_.knn_search(p.cuda(), q.cuda(), k, algo="tiled")
-    for name, a, b in zip(("d_p", "i_p", "knn_p", "d_q", "i_q", "knn_q"), got, want):
-        if a is None:
-            assert b is None
-            continue
-        assert torch.equal(a, b), "%s differs on %s: %d of %d" % (name, kind, int((a != b).sum()), a.numel())
+    for algo in ("grid", "auto"):
+        got = F_.knn_search(p.cuda(), q.cuda(), k, algo=algo)
+        for name, a, b in zip(("d_p", "i_p", "knn_p", "d_q", "i_q", "knn_q"), got, want):
+            if a is None:
+                assert b is None
+                continue
+            assert torch.equal(a, b), "%s (%s) differs on %s: %d of %d" % (name, algo, kind, int((a != b).sum()), a.numel())
     # and against exact fp64 distances (ties broken by index, like torch.min on the oracle's matrix)
     d = mesh_ops.p2p_distance(p.double(), q.double())
     dd = torch.gather(d, 2, got[1].long().cpu().unsqueeze(2)).squeeze(2)
@@ -277,3 +278,57 @@ def test_gt_sampling_cdf_cache(lib):
     assert owner._mrb_face_cdf[0] != key
     want, _ = F_.sample_points(verts, faces, vi, fi, 500, seed=7)
     assert torch.equal(c3, want)
+
+
+def test_validate_batch_on_eval_dict_vs_oracle(lib):
+    """the device path of reference ``validate`` (eval_utils.py:160-164): batched_mesh_loss over ALL FOUR
+    position sets of an eval-mode output dict (injected draws, vs the fp64 oracle) + F1@tau from the NN distances (vs dense
+    fp64 distances on the same clouds)."""
+    from oracle import cubify_np
+    from meshrcnn_b200 import functional as F_, synthetic
+    from meshrcnn_b200.eval_utils import validate_batch
+    from meshrcnn_b200.mesh_sampling import normalize_mesh
+    from meshrcnn_b200.pipeline import MeshTargets, RefinementHead
+    B, V, n, k = 2, 12, 1500, 10
+    vox = synthetic.blob_voxels(B, V, 2)
+    fmap = synthetic.feature_maps(B, [synthetic.PIX3D_MAP], 2)[0] * 0.02
+    torch.manual_seed(3)
+    head = RefinementHead("pix3d", cubify_threshold=0.2).cuda().eval()
+    with torch.no_grad():
+        for prm in head.parameters():
+            prm.mul_(0.2)
+        out = head(vox.cuda(), fmap.cuda(), [(224, 224)] * B)
+    out["voxels"] = vox.cuda()
+    gverts, gvi, gfaces, gfi, _ = cubify_np.cubify(synthetic.blob_voxels(B, V, 1002).numpy(), 0.5)
+    gt_pos = torch.cat([mesh_ops.normalize_cloud(v) for v in torch.from_numpy(gverts).double().split(gvi)])
+    batch = MeshTargets(gt_pos.float().cuda(), torch.from_numpy(gfaces).cuda(), gvi, gfi)
+    batch.voxels = (synthetic.blob_voxels(B, V, 1002) > 0.5).float().cuda()
+    vi, fi = out["vertice_index"], out["face_index"]
+    faces, adj = out["faces"].cpu(), out["edge_index"].cpu()
+    rnd, want = [], [0.0, 0.0, 0.0]
+    for s, pos in enumerate(out["vertex_positions"]):
+        p64 = pos.cpu().double()
+        u, x2, x1 = synthetic.sampling_randomness(B, n, 30 + s)
+        ug, x2g, x1g = synthetic.sampling_randomness(B, n, 40 + s)
+        fp = torch.stack([mesh_ops.face_cdf_draw(v, f, u[b]) for b, (v, f) in enumerate(zip(p64.split(vi), faces.split(fi)))])
+        fg = torch.stack([mesh_ops.face_cdf_draw(v, f, ug[b]) for b, (v, f) in
+                          enumerate(zip(gt_pos.split(gvi), torch.from_numpy(gfaces).split(gfi)))])
+        rnd.append((dict(face_idx=fp, xi2=x2, xi1=x1), dict(face_idx=fg, xi2=x2g, xi1=x1g)))
+        c, nl, e, _ = mesh_ops.mesh_loss_with(p64, faces, adj, vi, fi, gt_pos, torch.from_numpy(gfaces), gvi, gfi,
+                                              (fp, x2.double(), x1.double()), (fg, x2g.double(), x1g.double()), float(n), k,
+                                              canonical_signs=True)
+        want = [want[0] + float(c), want[1] + float(nl), want[2] + float(e)]
+    res = validate_batch(out, batch, float(n), k, randomness=rnd, f1_seed=11)
+    assert len(out["vertex_positions"]) == 4
+    for name, w in zip(("chamfer_loss", "normal_loss", "edge_loss"), want):
+        assert abs(float(res[name]) - w) <= 1e-4 * abs(w) + 1e-7, (name, float(res[name]), w)
+    bce = torch.nn.functional.binary_cross_entropy(vox.double(), batch.voxels.cpu().double())
+    assert abs(float(res["voxel_loss"]) - float(bce)) <= 1e-5 * float(bce)
+    # F1@tau: same clouds (same seeds), dense fp64 distances
+    cp, _ = F_.sample_points(out["vertex_positions"][-1], out["faces"], vi, fi, n, seed=11)
+    cg, _ = F_.sample_points(batch.meshes[0], batch.meshes[1], gvi, gfi, n, seed=12)
+    d = mesh_ops.p2p_distance(cp.cpu().double(), cg.cpu().double()).clamp_min(0).sqrt()
+    for tau in (0.1, 0.3, 0.5):
+        pr, rc = (d.min(2).values < tau).double().mean(1), (d.min(1).values < tau).double().mean(1)
+        f1 = float((100 * 2 * pr * rc / (pr + rc).clamp_min(1e-8)).mean())
+        assert abs(float(res["f1@%g" % tau]) - f1) <= 0.2, (tau, float(res["f1@%g" % tau]), f1)     # points within 1e-6 of tau may flip
