@@ -506,6 +506,9 @@ __device__ __forceinline__ void key_sort2(float& da, int& ia, float& db, int& ib
 //     lane s.
 // A pass is final when K keys were found and the k-th distance is <= r^2; otherwise r grows to that distance (or doubles)
 // and the search restarts with the old k-th distance as a filter.  grid: (ceil(P / (4 * GRID_QPW)), B).
+#ifndef MRB_GRID_SKIP_UNDERFULL
+#define MRB_GRID_SKIP_UNDERFULL 1
+#endif
 #ifndef MRB_GRID_MINB
 #define MRB_GRID_MINB 10    // 48 registers (measured: 1 -> 78 regs 0.77 ms, 10 -> 0.67, 12 -> 0.65, 16 -> 0.66 ms per call at config 5)
 #endif
@@ -540,6 +543,8 @@ __global__ void __launch_bounds__(GRID_THREADS, MRB_GRID_MINB) k_nn_grid(const f
             const int z0 = cell_of(ap.z - rr, h.lo[2], h.inv[2], G), z1 = cell_of(ap.z + rr, h.lo[2], h.inv[2], G);
             const int ny = y1 - y0 + 1, nrow = ny * (z1 - z0 + 1);
             const float inv_ny = 1.0f / (float)ny;
+            const bool all = (h.inv[0] == 0.f || (x0 == 0 && x1 == G - 1)) && (h.inv[1] == 0.f || (y0 == 0 && y1 == G - 1)) &&
+                             (h.inv[2] == 0.f || (z0 == 0 && z1 == G - 1));
             ld = FLT_MAX; li = NONE;
             for (int rbase = 0; rbase < nrow; rbase += 32) {
                 int s = 0, cnt = 0;
@@ -551,6 +556,11 @@ __global__ void __launch_bounds__(GRID_THREADS, MRB_GRID_MINB) k_nn_grid(const f
                 }
                 const int incl = warp_inclusive_scan(cnt);
                 const int m = __shfl_sync(FULL, incl, 31);
+#if MRB_GRID_SKIP_UNDERFULL
+                // The cell offsets already tell how many candidates the box holds: a box (all its rows fit this batch) with
+                // fewer than K of them cannot fill the list, so the pass could not be final -- grow r without reading a point.
+                if (nrow <= 32 && m < K && !all) break;
+#endif
                 const int shift = s - (incl - cnt);                // candidate t of this row sits at bq[t + shift]
                 for (int base = 0; base < m; base += 32 * GRID_CH) {
                     float vd[GRID_CH + 1];
@@ -605,8 +615,6 @@ __global__ void __launch_bounds__(GRID_THREADS, MRB_GRID_MINB) k_nn_grid(const f
             const float kd = __shfl_sync(FULL, ld, K - 1);
             const bool full = __shfl_sync(FULL, li, K - 1) != NONE;
             if (full && kd <= r * r) break;
-            const bool all = (h.inv[0] == 0.f || (x0 == 0 && x1 == G - 1)) && (h.inv[1] == 0.f || (y0 == 0 && y1 == G - 1)) &&
-                             (h.inv[2] == 0.f || (z0 == 0 && z1 == G - 1));
             if (all) break;
             if (full) {
                 r = fmaf(sqrtf(kd), 1e-6f, sqrtf(kd));

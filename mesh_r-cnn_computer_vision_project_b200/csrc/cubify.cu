@@ -63,6 +63,9 @@ static Dims make_dims(int B, int Z, int Y, int X) {
 struct Workspace {
     uint8_t* ff;      // [B*nvox] 6 face-flag bits per voxel
     int32_t* rank;    // [B*nlat] vertex id per used lattice point
+    uint32_t* lmask;  // [B*nlat] 27-bit neighbour mask per lattice point (0 <=> not a vertex), written by the count pass
+    int32_t* segBase; // [3][B+1] first face-quad / vertex / directed edge of every mesh (+ totals): the chunk counters above
+                      // are scanned per mesh (local offsets), the per-mesh bases are added by the emit kernels
     int32_t* faceOff; // [B*6*nchF + 1]
     int32_t* vertOff; // [B*nchL + 1]
     int32_t* edgeOff; // [B*nchL + 1]
@@ -82,9 +85,12 @@ static size_t carve(const Dims& d, void* base, Workspace* ws) {
     void* p2 = take(((size_t)d.B * 6 * d.nchF + 1) * 4);
     void* p3 = take(((size_t)d.B * d.nchL + 1) * 4);
     void* p4 = take(((size_t)d.B * d.nchL + 1) * 4);
+    void* p5 = take((size_t)d.B * d.nlat * 4);
+    void* p6 = take((size_t)3 * (d.B + 1) * 4);
     if (ws) {
+        ws->segBase = (int32_t*)p6;
         ws->ff = (uint8_t*)p0; ws->rank = (int32_t*)p1; ws->faceOff = (int32_t*)p2;
-        ws->vertOff = (int32_t*)p3; ws->edgeOff = (int32_t*)p4;
+        ws->vertOff = (int32_t*)p3; ws->edgeOff = (int32_t*)p4; ws->lmask = (uint32_t*)p5;
     }
     return off;
 }
@@ -126,32 +132,42 @@ __global__ void __launch_bounds__(CH) k_faceflags(const float* __restrict__ prob
     }
 }
 
-// neighbour mask (27 bits) of lattice point (lz,ly,lx) of mesh b; 0 <=> not a vertex
-__device__ __forceinline__ uint32_t lattice_mask(const uint8_t* __restrict__ ffb, const Dims& d, int lz, int ly, int lx) {
+// neighbour mask (27 bits) of lattice point (lz,ly,lx) of mesh b; 0 <=> not a vertex.  tab[s][f] = OR of kLatMask[s][k] over
+// the set bits k of the 6-bit face-flag byte f (built once per block in shared memory): one lookup per adjacent voxel
+// instead of six predicated ORs.
+__device__ __forceinline__ uint32_t lattice_mask(const uint8_t* __restrict__ ffb, const uint32_t (*tab)[64], const Dims& d, int lz,
+                                                 int ly, int lx) {
     uint32_t m = 0;
 #pragma unroll
     for (int a = 0; a < 8; ++a) {
         const int vz = lz - 1 + ((a >> 2) & 1), vy = ly - 1 + ((a >> 1) & 1), vx = lx - 1 + (a & 1);
         if (vz < 0 || vz >= d.Z || vy < 0 || vy >= d.Y || vx < 0 || vx >= d.X) continue;
         const unsigned f = ffb[((size_t)vz * d.Y + vy) * d.X + vx];
-        if (!f) continue;
-        const int s = 7 - a;   // corner position relative to that voxel: (1-az, 1-ay, 1-ax)
-#pragma unroll
-        for (int k = 0; k < 6; ++k)
-            if ((f >> k) & 1u) m |= kLatMask[s][k];
+        m |= tab[7 - a][f];        // corner position relative to that voxel: (1-az, 1-ay, 1-ax)
     }
     return m;
 }
 
-// pass 1b: per-(mesh, lattice chunk) vertex and directed-edge counts
+// pass 1b: per-(mesh, lattice chunk) vertex and directed-edge counts; the masks are kept for the emit pass
 __global__ void __launch_bounds__(CH) k_lattice_count(Dims d, Workspace ws) {
     __shared__ int scratch[33];
+    __shared__ uint32_t tab[8][64];
+    {
+        const int s8 = threadIdx.x >> 6, f = threadIdx.x & 63;      // CH == 512 == 8 * 64 table entries
+        uint32_t m = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            if ((f >> k) & 1) m |= kLatMask[s8][k];
+        tab[s8][f] = m;
+    }
+    __syncthreads();
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int l = chunk * CH + threadIdx.x;
     uint32_t m = 0;
     if (l < d.nlat) {
         const int lx = l % d.LX, ly = (l / d.LX) % d.LY, lz = l / (d.LX * d.LY);
-        m = lattice_mask(ws.ff + (size_t)b * d.nvox, d, lz, ly, lx);
+        m = lattice_mask(ws.ff + (size_t)b * d.nvox, tab, d, lz, ly, lx);
+        ws.lmask[(size_t)b * d.nlat + l] = m;
     }
     const int nv = __syncthreads_count(m != 0);
     const int ne = block_sum<int>(__popc(m), scratch);
@@ -161,51 +177,67 @@ __global__ void __launch_bounds__(CH) k_lattice_count(Dims d, Workspace ws) {
     }
 }
 
-// pass 1c: exclusive scans of the three count arrays (one block each) + per-mesh totals.
+// pass 1c: exclusive scans of the three chunk-count arrays, two levels: one block per (mesh, array) scans that mesh's
+// segment in place (coalesced through shared memory) and records its total; one block then scans the B totals per array
+// and fills meta.  (A single-block scan of the 83k face counters of 64 x 48^3 took 65 us.)
 // meta layout (int64): [0]=SV [1]=SF [2]=E [3]=unused, then v_count[B], f_count[B], v_offset[B], f_offset[B]
-__global__ void __launch_bounds__(1024) k_scan(Dims d, Workspace ws, long long* __restrict__ meta) {
+constexpr int SEG_THREADS = 256, SEG_PER = 8;
+__global__ void __launch_bounds__(SEG_THREADS) k_scan_seg(Dims d, Workspace ws) {
+    __shared__ int buf[SEG_THREADS * SEG_PER];
     __shared__ int scratch[33];
-    int32_t* arr;
-    int n;
-    if (blockIdx.x == 0) { arr = ws.faceOff; n = d.B * 6 * d.nchF; }
-    else if (blockIdx.x == 1) { arr = ws.vertOff; n = d.B * d.nchL; }
-    else { arr = ws.edgeOff; n = d.B * d.nchL; }
+    const int b = blockIdx.x, which = blockIdx.y;
+    const int len = which == 0 ? 6 * d.nchF : d.nchL;
+    int32_t* arr = (which == 0 ? ws.faceOff : (which == 1 ? ws.vertOff : ws.edgeOff)) + (size_t)b * len;
     int carry = 0;
-    constexpr int PER = 8;                       // consecutive elements per thread: 8192 per block-scan round
-    for (int base = 0; base < n; base += 1024 * PER) {
-        const int i0 = base + threadIdx.x * PER;
-        int vals[PER], sum = 0;
+    for (int base = 0; base < len; base += SEG_THREADS * SEG_PER) {
 #pragma unroll
-        for (int u = 0; u < PER; ++u) {
-            vals[u] = (i0 + u < n) ? arr[i0 + u] : 0;
-            sum += vals[u];
+        for (int u = 0; u < SEG_PER; ++u) {
+            const int i = base + u * SEG_THREADS + threadIdx.x;
+            buf[u * SEG_THREADS + threadIdx.x] = i < len ? arr[i] : 0;
         }
+        __syncthreads();
+        int vals[SEG_PER], sum = 0;
+#pragma unroll
+        for (int u = 0; u < SEG_PER; ++u) { vals[u] = buf[threadIdx.x * SEG_PER + u]; sum += vals[u]; }
         int total;
         int run = carry + block_exclusive_scan(sum, scratch, &total);
 #pragma unroll
-        for (int u = 0; u < PER; ++u) {
-            if (i0 + u < n) arr[i0 + u] = run;
-            run += vals[u];
+        for (int u = 0; u < SEG_PER; ++u) { buf[threadIdx.x * SEG_PER + u] = run; run += vals[u]; }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < SEG_PER; ++u) {
+            const int i = base + u * SEG_THREADS + threadIdx.x;
+            if (i < len) arr[i] = buf[u * SEG_THREADS + threadIdx.x];
         }
         carry += total;
         __syncthreads();
     }
-    if (threadIdx.x == 0) arr[n] = carry;
-    __syncthreads();
-    if (blockIdx.x == 0) {
-        if (threadIdx.x == 0) meta[1] = 2LL * carry;
-        for (int b = threadIdx.x; b < d.B; b += 1024) {
-            meta[4 + d.B + b] = 2LL * (arr[(b + 1) * 6 * d.nchF] - arr[b * 6 * d.nchF]);
-            meta[4 + 3 * d.B + b] = 2LL * arr[b * 6 * d.nchF];
+    if (threadIdx.x == 0) ws.segBase[which * (d.B + 1) + b] = carry;      // the segment total; k_scan_top turns it into a base
+}
+
+__global__ void __launch_bounds__(1024) k_scan_top(Dims d, Workspace ws, long long* __restrict__ meta) {
+    __shared__ int scratch[33];
+    const int which = blockIdx.x;
+    int32_t* seg = ws.segBase + which * (d.B + 1);
+    int carry = 0;
+    for (int base = 0; base < d.B; base += 1024) {
+        const int b = base + threadIdx.x;
+        const int cnt = b < d.B ? seg[b] : 0;
+        int total;
+        const int ex = carry + block_exclusive_scan(cnt, scratch, &total);
+        if (b < d.B) {
+            seg[b] = ex;
+            if (which == 0) { meta[4 + d.B + b] = 2LL * cnt; meta[4 + 3 * d.B + b] = 2LL * ex; }
+            else if (which == 1) { meta[4 + b] = cnt; meta[4 + 2 * d.B + b] = ex; }
         }
-    } else if (blockIdx.x == 1) {
-        if (threadIdx.x == 0) meta[0] = carry;
-        for (int b = threadIdx.x; b < d.B; b += 1024) {
-            meta[4 + b] = arr[(b + 1) * d.nchL] - arr[b * d.nchL];
-            meta[4 + 2 * d.B + b] = arr[b * d.nchL];
-        }
-    } else {
-        if (threadIdx.x == 0) { meta[2] = carry; meta[3] = 0; }
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        seg[d.B] = carry;
+        if (which == 0) meta[1] = 2LL * carry;
+        else if (which == 1) meta[0] = carry;
+        else { meta[2] = carry; meta[3] = 0; }
     }
 }
 
@@ -221,28 +253,28 @@ __global__ void __launch_bounds__(CH) k_emit_verts(Dims d, Workspace ws, float* 
     uint32_t m = 0;
     int lx = 0, ly = 0, lz = 0;
     if (l < d.nlat) {
-        lx = l % d.LX; ly = (l / d.LX) % d.LY; lz = l / (d.LX * d.LY);
-        m = lattice_mask(ws.ff + (size_t)b * d.nvox, d, lz, ly, lx);
+        m = ws.lmask[(size_t)b * d.nlat + l];          // computed once by k_lattice_count
+        if (m) { lx = l % d.LX; ly = (l / d.LX) % d.LY; lz = l / (d.LX * d.LY); }
     }
     int tot;
     const int exv = block_exclusive_scan(m != 0 ? 1 : 0, scratch, &tot);
     __syncthreads();
     const int exe = block_exclusive_scan(__popc(m), scratch, &tot);
     if (m) {
-        const int vid = ws.vertOff[(size_t)b * d.nchL + chunk] + exv;
+        const int vid = ws.segBase[(d.B + 1) + b] + ws.vertOff[(size_t)b * d.nchL + chunk] + exv;
         ws.rank[(size_t)b * d.nlat + l] = vid;
         // (z,y,x) half-integers rotated 90 deg about axis 0: (z, x, -y)  (layers.py:465-467, exact in fp32)
         verts[3 * (size_t)vid + 0] = (float)lz - 0.5f;
         verts[3 * (size_t)vid + 1] = (float)lx - 0.5f;
         verts[3 * (size_t)vid + 2] = -((float)ly - 0.5f);
-        rowptr[vid] = ws.edgeOff[(size_t)b * d.nchL + chunk] + exe;
+        rowptr[vid] = ws.segBase[2 * (d.B + 1) + b] + ws.edgeOff[(size_t)b * d.nchL + chunk] + exe;
         vert_mesh[vid] = b;
         vmask[vid] = m;
         vlat[vid] = b * d.nlat + l;
     }
     if (b == d.B - 1 && chunk == d.nchL - 1 && threadIdx.x == 0) {
-        const int SV = ws.vertOff[(size_t)d.B * d.nchL];
-        rowptr[SV] = ws.edgeOff[(size_t)d.B * d.nchL];
+        const int SV = ws.segBase[(d.B + 1) + d.B];
+        rowptr[SV] = ws.segBase[2 * (d.B + 1) + d.B];
     }
 }
 
@@ -288,11 +320,20 @@ __global__ void __launch_bounds__(ADJ_BLOCK) k_emit_adj(Dims d, Workspace ws, in
 
 // pass 2c: faces in (b, dir, z, y, x) order, two triangles (c0,c1,c2),(c0,c2,c3) per quad, per-mesh local ids.
 // A quad is 6 int64 = 48 contiguous bytes and consecutive flagged lanes write consecutive quads, so every thread stores its
-// quad straight from registers as three 16-byte vectors (a warp covers up to 1.5 KB of contiguous output); one barrier for
-// the per-warp offsets of all six directions.
+// quad straight from registers as three 16-byte vectors (a warp covers up to 1.5 KB of contiguous output).  The kernel was
+// instruction bound (1 080 warp instructions per 32 voxels): now the 8 corner ranks of a voxel are loaded once (not 4 per
+// quad with their own index arithmetic), the quad corners are compile-time picks among them, and the per-warp output offsets
+// of all six directions come from one shared-memory prefix pass instead of a serial sum per (thread, direction).
+__device__ __forceinline__ constexpr int corner_id(int k, int j) {
+    // kCorner[k][j] as cz*4 + cy*2 + cx (same table as the __constant__ one above, usable in constant expressions)
+    constexpr int T[6][4] = {{0, 1, 2, 3}, {4, 5, 6, 7}, {4, 5, 0, 1}, {2, 3, 6, 7}, {4, 0, 6, 2}, {1, 5, 3, 7}};
+    return T[k][j];
+}
+
 __global__ void __launch_bounds__(CH) k_emit_faces(Dims d, Workspace ws, const long long* __restrict__ meta,
                                                    long long* __restrict__ faces) {
-    __shared__ int wtot[6][CH / 32];
+    constexpr int NW = CH / 32;
+    __shared__ int wtot[6][NW];
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int v = chunk * CH + threadIdx.x;
     const unsigned f = (v < d.nvox) ? ws.ff[(size_t)b * d.nvox + v] : 0u;
@@ -304,26 +345,31 @@ __global__ void __launch_bounds__(CH) k_emit_faces(Dims d, Workspace ws, const l
         if (lane_id() == 0) wtot[k][warp_id()] = __popc(bal);
     }
     __syncthreads();
+    if (threadIdx.x < 6 * 32) {                    // warp k: exclusive prefix of direction k's per-warp totals
+        const int k = warp_id();
+        const int mine = lane_id() < NW ? wtot[k][lane_id()] : 0;
+        const int inc = warp_inclusive_scan(mine);
+        __syncwarp();
+        if (lane_id() < NW) wtot[k][lane_id()] = inc - mine;
+    }
+    __syncthreads();
     if (f == 0u) return;
     const int x = v % d.X, y = (v / d.X) % d.Y, z = v / (d.X * d.Y);
     const int voff = (int)meta[4 + 2 * d.B + b];
-    const int32_t* rk = ws.rank + (size_t)b * d.nlat;
+    const int32_t* rk = ws.rank + (size_t)b * d.nlat + ((size_t)z * d.LY + y) * d.LX + x;
+    const int sY = d.LX, sZ = d.LX * d.LY;
+    long long r[8];                                // local vertex ids of the voxel's 8 lattice corners (unused corners hold junk)
+#pragma unroll
+    for (int a = 0; a < 8; ++a) r[a] = (long long)(rk[((a >> 2) & 1) * sZ + ((a >> 1) & 1) * sY + (a & 1)] - voff);
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
         if (!((f >> k) & 1u)) continue;
-        int before = 0;
-        for (int w = 0; w < warp_id(); ++w) before += wtot[k][w];
-        long long c[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int lz = z + kCorner[k][j][0], ly = y + kCorner[k][j][1], lx = x + kCorner[k][j][2];
-            c[j] = rk[((size_t)lz * d.LY + ly) * d.LX + lx] - voff;
-        }
-        const long long q = ws.faceOff[((size_t)b * 6 + k) * d.nchF + chunk] + before + pre[k];
+        const long long q = ws.segBase[b] + ws.faceOff[((size_t)b * 6 + k) * d.nchF + chunk] + wtot[k][warp_id()] + pre[k];
+        const long long c0 = r[corner_id(k, 0)], c1 = r[corner_id(k, 1)], c2 = r[corner_id(k, 2)], c3 = r[corner_id(k, 3)];
         longlong2* o = reinterpret_cast<longlong2*>(faces + q * 6);          // 48-byte quads: 16-byte aligned
-        o[0] = make_longlong2(c[0], c[1]);
-        o[1] = make_longlong2(c[2], c[0]);
-        o[2] = make_longlong2(c[2], c[3]);
+        o[0] = make_longlong2(c0, c1);
+        o[1] = make_longlong2(c2, c0);
+        o[2] = make_longlong2(c2, c3);
     }
 }
 
@@ -352,7 +398,8 @@ extern "C" int mrb_cubify_count(const float* probs, int B, int Z, int Y, int X, 
     if (from_logits) k_faceflags<true><<<dim3(d.nchF, B), CH, 0, stream>>>(probs, threshold, d, ws);
     else k_faceflags<false><<<dim3(d.nchF, B), CH, 0, stream>>>(probs, threshold, d, ws);
     k_lattice_count<<<dim3(d.nchL, B), CH, 0, stream>>>(d, ws);
-    k_scan<<<3, 1024, 0, stream>>>(d, ws, meta);
+    k_scan_seg<<<dim3(B, 3), SEG_THREADS, 0, stream>>>(d, ws);
+    k_scan_top<<<3, 1024, 0, stream>>>(d, ws, meta);
     return check_launch("cubify_count");
 }
 
