@@ -179,7 +179,7 @@ def make_host_inputs(name, B, rank, world, balance=True):
 class HeadWorkload:
     """Cubify + 3 refinement stages + losses + backward (+ the per-stage gradient all-reduce) on this rank's shard."""
 
-    def __init__(self, name, dev, rank, world):
+    def __init__(self, name, dev, rank, world, map_dtype=torch.float32):
         from meshrcnn_b200.layers import Cubify
         from meshrcnn_b200.mesh_sampling import normalize_mesh
         from meshrcnn_b200.pipeline import MeshTargets, RefinementHead
@@ -196,6 +196,8 @@ class HeadWorkload:
         gv, gvi, gfaces, gfi, _ = Cubify(0.5)(gt_vox_h.to(dev))
         self.gt = MeshTargets(torch.cat([normalize_mesh(v) for v in gv.split(gvi)]), gfaces, gvi, gfi)
         self.vox_d = self.vox_h.to(dev)
+        if map_dtype != torch.float32:                               # bf16 feature-map mode (north star: rtol 2e-2)
+            self.fmaps_h = [f.to(map_dtype) for f in self.fmaps_h]
         self.fmaps_d = [f.to(dev).requires_grad_() for f in self.fmaps_h]
 
     def step(self, vox_d=None, fmaps_d=None, exchange=True):
@@ -390,6 +392,26 @@ def extra_shapenet_shard(dev, rank, world, pool, flush, sync_all, steps, peaks):
                "peak_mem_GB": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2),
                "collective": "NCCL all-reduce(SUM), one bucket per stage, issued from backward hooks" if world > 1 else "none (N = 1)",
                "breakdown_ms": {k: v for k, v in list(bd.items())[:14]}}
+    del wl
+    torch.cuda.empty_cache()
+    return out
+
+
+def extra_bf16_maps(dev, rank, world, pool, flush, sync_all, steps):
+    """The headline workload with the feature maps held in bf16 (half the map bytes in HBM and over PCIe; positions,
+    weights, accumulation and every loss stay fp32; parity: rtol 2e-2, tests/test_layers_gpu.py)."""
+    wl = HeadWorkload("pix3d", dev, rank, world, map_dtype=torch.bfloat16)
+    for _ in range(3):
+        wl.step()
+    sync_all()
+    ms, launches = timed_resident(wl, pool, steps, flush, sync_all)
+    total = reduce_max_ms(sum(ms), dev, world)
+    out = None
+    if rank == 0:
+        out = {"workload": (WORKLOADS["pix3d"]["label"] % wl.B) + " -- feature maps in bf16", "metric": "meshes/sec (fwd+bwd, 3 refine stages)",
+               "value": round(wl.B * world * steps / (total * 1e-3), 1), "unit": "meshes/s", "n_gpus": world, "steps": steps, "warmup": 3,
+               "ms_per_step": round(total / steps, 3), "dtype": "bf16 feature maps, f32 everything else",
+               "map_bytes_per_step": int(sum(f.numel() * 2 for f in wl.fmaps_h)), "gpu_launches": int(launches)}
     del wl
     torch.cuda.empty_cache()
     return out
@@ -598,6 +620,7 @@ def run_cuda(args):
         del wl
         torch.cuda.empty_cache()
         ex_steps = max(3, min(steps, 10))
+        extras["configs[1] with bf16 feature maps"] = extra_bf16_maps(dev, rank, world, pool, flush, sync_all, ex_steps)
         extras["configs[2]"] = extra_shapenet_shard(dev, rank, world, pool, flush, sync_all, ex_steps, peaks)
         extras["configs[3]"] = extra_cubify_stress(dev, rank, world, pool, flush, sync_all, peaks)
         extras["configs[4]"] = extra_chamfer_sweep(dev, rank, world, pool, flush, sync_all, fma_peak)

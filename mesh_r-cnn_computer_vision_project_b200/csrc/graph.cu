@@ -73,13 +73,13 @@ __global__ void k_coo_hist(const long long* __restrict__ rows, int E, int n, int
 
 __global__ void k_coo_fill(const long long* __restrict__ rows, const long long* __restrict__ cols, int E, int n,
                            const int32_t* __restrict__ rowptr, int32_t* __restrict__ cursor,
-                           const int32_t* __restrict__ flags, int32_t* __restrict__ col) {
+                           int32_t* __restrict__ flags, int32_t* __restrict__ col) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
     const long long r = rows[e];
     if (r < 0 || r >= n) return;
     long long c = cols[e];
-    if (c < 0 || c >= n) c = r;   // flagged separately; keep memory safe
+    if (c < 0 || c >= n) { atomicOr(flags + 1, 1); c = r; }   // out-of-range column: flagged like a bad row; keep memory safe
     if (flags[0] == 0) {
         col[e] = (int32_t)c;      // already row-sorted: CSR order == COO order (deterministic)
     } else {

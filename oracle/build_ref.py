@@ -9,7 +9,7 @@ it travels with the working tree like a built ``.so``).  ``__graft_entry__.build
     python -m oracle.build_ref              # dev container only; a no-op when /root/reference is absent
 
 Files: meshRCNN/layers.py, meshRCNN/loss_functions.py, meshRCNN/utils.py,
-utils/mesh_sampling.py, utils/process.py, utils/rotation.py.  They are imported behind the shims of
+utils/mesh_sampling.py, utils/process.py, utils/rotation.py; plus meshRCNN/shapenet_model.py for the drop-in test.  They are imported behind the shims of
 ``oracle/ref_import.py`` (stub packages, symeig -> eigh, stable argsort); nothing in them is edited.
 """
 import filecmp
@@ -21,7 +21,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.environ.get("MESHRCNN_REFERENCE_SRC", "/root/reference")
 DST = os.path.join(HERE, "_ref")
 FILES = ("meshRCNN/layers.py", "meshRCNN/loss_functions.py", "meshRCNN/utils.py", "utils/mesh_sampling.py",
-         "utils/process.py", "utils/rotation.py")
+         "utils/process.py", "utils/rotation.py",
+         # the reference's own model file: tests/test_dropin_gpu.py executes it UNMODIFIED with `.layers` / `.loss_functions`
+         # bound to this repo's modules (the drop-in claim of INTEGRATION.md, checked on the GPU box)
+         "meshRCNN/shapenet_model.py")
 
 
 def build_ref(verbose: bool = False) -> bool:

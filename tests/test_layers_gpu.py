@@ -664,3 +664,25 @@ def test_fused_stages_equal_literal_stages(lib, model):
         w = b[k].double()
         err = float((a[k].double() - w).norm() / max(float(w.norm()), 1e-30))
         assert err <= 1e-4, (k, err)
+
+
+def test_foreign_coo_validation_and_topology_cache(lib):
+    """out-of-range vertex ids in a foreign edge list raise IndexError (like the reference's indexing) instead of
+    being silently rewritten, and an in-place edit of a cached edge list invalidates its CSR."""
+    from meshrcnn_b200 import functional as F_, topology
+    x = torch.randn(6, 8).cuda()
+    good = torch.tensor([[0, 1, 2, 3, 4, 5], [1, 0, 3, 2, 5, 4]]).cuda()
+    out = F_.aggregate_neighbours(good, x)
+    assert torch.equal(out.cpu(), x.cpu()[[1, 0, 3, 2, 5, 4]])
+    for bad in (torch.tensor([[0, 1, 7], [1, 0, 2]]), torch.tensor([[0, 1, 2], [1, 0, 6]]), torch.tensor([[0, -1], [1, 0]])):
+        with pytest.raises(IndexError):
+            F_.aggregate_neighbours(bad.cuda(), x)
+    t0 = topology.from_coo(good, 6)
+    assert topology.from_coo(good, 6) is t0                     # cached
+    good[1, 0] = 2                                              # in-place edit: edge (0,1) -> (0,2)
+    t1 = topology.from_coo(good, 6)
+    assert t1 is not t0
+    want = x.cpu()[[2, 0, 3, 2, 5, 4]]
+    assert torch.equal(F_.aggregate_neighbours(good, x).cpu(), want)
+    empty = torch.zeros(2, 0, dtype=torch.int64).cuda()
+    assert float(F_.aggregate_neighbours(empty, x).abs().sum()) == 0.0
