@@ -54,8 +54,10 @@ if mode == "old":
         one()
     torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    segs = []            # cudaMalloc'ed segments of the caching allocator after every step
     for a, b in ev:
         flush.zero_(); a.record(); ta = time.perf_counter(); one(); marks.append((ta, time.perf_counter())); b.record()
+        segs.append(torch.cuda.memory_stats(dev)["segment.all.allocated"])
     torch.cuda.synchronize()
     ms = [a.elapsed_time(b) for a, b in ev]
 else:
@@ -82,6 +84,8 @@ print("watchdog gaps > 20 ms:", len(gaps))
 for g, before, after in gaps[:10]:
     print("  gap %.1f ms\n    before: %s\n    after:  %s" % (g * 1e3, before, after))
 if marks:
+    grew = [i for i in range(1, len(segs)) if segs[i] > segs[i - 1]]
+    print("steps during which the caching allocator called cudaMalloc (new segments):", grew, "segments:", segs[0], "->", segs[-1])
     for i, x in enumerate(ms):
         if x > 3 * med:
             ta, tb = marks[i]
