@@ -272,6 +272,17 @@ int mrb_normal_loss_fwd(const float* na, const float* nb, int B, int P, int Q, c
                         double* acc2, float* out2, void* stream);
 int mrb_normal_loss_bwd(const float* na, const float* nb, int B, int P, int Q, const int32_t* idx_a, const int32_t* idx_b,
                         const float* g0, const float* g1, float* gna, float* gnb, void* stream);
+/* Scaled totals (what mesh_loss returns, loss_functions.py:66,72): out1[0] = scale * (sum_i |na.nb| + sum_j |nb.na|) and its
+ * backward with the single upstream gradient *g -- the add / negate / divide chain of the reference folded into the kernels. */
+int mrb_normal_loss_total_fwd(const float* na, const float* nb, int B, int P, int Q, const int32_t* idx_a, const int32_t* idx_b,
+                              double scale, double* acc2, float* out1, void* stream);
+int mrb_normal_loss_total_bwd(const float* na, const float* nb, int B, int P, int Q, const int32_t* idx_a, const int32_t* idx_b,
+                              const float* g, float scale, float* gna, float* gnb, void* stream);
+/* Scalar glue of the loss (sums over the refinement stages, the weighted total of utils/train_utils.py:208-225):
+ * out[0] = sum_i w[i] * *xs[i]   and   out[i] = *g * w[i]   (n <= 16; xs_host: HOST array of n device pointers,
+ * w_host: HOST array of n weights -- both are read during the call). */
+int mrb_scalar_combine(const void* xs_host, const float* w_host, int n, float* out, void* stream);
+int mrb_scalar_scatter(const float* g, const float* w_host, int n, float* out, void* stream);
 int mrb_edge_loss_fwd(const float* pos, const long long* adj, long long E, double* acc, float* out, void* stream);
 int mrb_edge_loss_bwd(const float* pos, const long long* adj, long long E, const float* g, float* gpos, void* stream);
 

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256) k_normal_loss(const float* __restrict__ n
 __global__ void __launch_bounds__(256) k_normal_loss_bwd(const float* __restrict__ na, const float* __restrict__ nb, int P,
                                                          int Q, const int32_t* __restrict__ idx_a,
                                                          const int32_t* __restrict__ idx_b, const float* __restrict__ g0,
-                                                         const float* __restrict__ g1, float* __restrict__ gna,
+                                                         const float* __restrict__ g1, float scale, float* __restrict__ gna,
                                                          float* __restrict__ gnb) {
     const int batch = blockIdx.y;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -192,10 +192,10 @@ __global__ void __launch_bounds__(256) k_normal_loss_bwd(const float* __restrict
         float g;
         if (pass == 0) {
             if (t >= P) continue;
-            i = (size_t)batch * P + t; j = (size_t)batch * Q + idx_a[i]; g = *g0;
+            i = (size_t)batch * P + t; j = (size_t)batch * Q + idx_a[i]; g = scale * (*g0);
         } else {
             if (t >= Q) continue;
-            j = (size_t)batch * Q + t; i = (size_t)batch * P + idx_b[j]; g = *g1;
+            j = (size_t)batch * Q + t; i = (size_t)batch * P + idx_b[j]; g = scale * (*g1);
         }
         const float dot = na[3 * i] * nb[3 * j] + na[3 * i + 1] * nb[3 * j + 1] + na[3 * i + 2] * nb[3 * j + 2];
         const float sg = dot > 0.f ? g : (dot < 0.f ? -g : 0.f);
@@ -208,6 +208,23 @@ __global__ void __launch_bounds__(256) k_normal_loss_bwd(const float* __restrict
 
 __global__ void k_finalize2(const double* __restrict__ acc, int n, double scale, float* __restrict__ out) {
     if (threadIdx.x < n) out[threadIdx.x] = (float)(acc[threadIdx.x] * scale);
+}
+__global__ void k_finalize_sum2(const double* __restrict__ acc, double scale, float* __restrict__ out) {
+    if (threadIdx.x == 0) out[0] = (float)((acc[0] + acc[1]) * scale);
+}
+
+// small scalar glue of the loss (sums over stages, the weighted total): one launch instead of a chain of ATen kernels
+constexpr int SC_MAX = 16;
+struct ScalarSet { const float* x[SC_MAX]; float w[SC_MAX]; int n; };
+__global__ void k_scalar_combine(const __grid_constant__ ScalarSet s, float* __restrict__ out) {
+    if (threadIdx.x == 0) {
+        float acc = 0.f;
+        for (int i = 0; i < s.n; ++i) acc = fmaf(s.w[i], *s.x[i], acc);
+        out[0] = acc;
+    }
+}
+__global__ void k_scalar_scatter(const float* __restrict__ g, const __grid_constant__ ScalarSet s, float* __restrict__ out) {
+    if (threadIdx.x < s.n) out[threadIdx.x] = (*g) * s.w[threadIdx.x];
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -285,8 +302,56 @@ extern "C" int mrb_normal_loss_bwd(const float* na, const float* nb, int B, int 
     MRB_REQUIRE(na && nb && idx_a && idx_b && g0 && g1, "normal_loss_bwd: null pointer");
     if (B == 0 || max(P, Q) == 0 || (!gna && !gnb)) return MRB_OK;
     k_normal_loss_bwd<<<dim3(ceil_div(max(P, Q), 256), B), 256, 0, (cudaStream_t)stream_>>>(na, nb, P, Q, idx_a, idx_b, g0,
-                                                                                           g1, gna, gnb);
+                                                                                           g1, 1.f, gna, gnb);
     return check_launch("normal_loss_bwd");
+}
+
+extern "C" int mrb_normal_loss_total_fwd(const float* na, const float* nb, int B, int P, int Q, const int32_t* idx_a,
+                                         const int32_t* idx_b, double scale, double* acc2, float* out1, void* stream_) {
+    MRB_REQUIRE(na && nb && idx_a && idx_b && acc2 && out1, "normal_loss_total_fwd: null pointer");
+    cudaStream_t s = (cudaStream_t)stream_;
+    cudaMemsetAsync(acc2, 0, 2 * sizeof(double), s);
+    if (B > 0 && max(P, Q) > 0)
+        k_normal_loss<<<dim3(ceil_div(max(P, Q), 256), B), 256, 0, s>>>(na, nb, P, Q, idx_a, idx_b, acc2);
+    k_finalize_sum2<<<1, 32, 0, s>>>(acc2, scale, out1);
+    return check_launch("normal_loss_total_fwd");
+}
+
+extern "C" int mrb_normal_loss_total_bwd(const float* na, const float* nb, int B, int P, int Q, const int32_t* idx_a,
+                                         const int32_t* idx_b, const float* g, float scale, float* gna, float* gnb,
+                                         void* stream_) {
+    MRB_REQUIRE(na && nb && idx_a && idx_b && g, "normal_loss_total_bwd: null pointer");
+    if (B == 0 || max(P, Q) == 0 || (!gna && !gnb)) return MRB_OK;
+    k_normal_loss_bwd<<<dim3(ceil_div(max(P, Q), 256), B), 256, 0, (cudaStream_t)stream_>>>(na, nb, P, Q, idx_a, idx_b, g, g,
+                                                                                           scale, gna, gnb);
+    return check_launch("normal_loss_total_bwd");
+}
+
+static int fill_scalar_set(ScalarSet& s, const float* const* xs_host, const float* w_host, int n, const char* what) {
+    MRB_REQUIRE(n >= 1 && n <= SC_MAX && w_host, "%s: 1..%d scalars", what, SC_MAX);
+    s.n = n;
+    for (int i = 0; i < SC_MAX; ++i) {
+        s.x[i] = (i < n && xs_host) ? xs_host[i] : nullptr;
+        s.w[i] = i < n ? w_host[i] : 0.f;
+    }
+    return MRB_OK;
+}
+
+extern "C" int mrb_scalar_combine(const void* xs_host, const float* w_host, int n, float* out, void* stream_) {
+    MRB_REQUIRE(xs_host && out, "scalar_combine: null pointer");
+    ScalarSet s;
+    if (int rc = fill_scalar_set(s, (const float* const*)xs_host, w_host, n, "scalar_combine")) return rc;
+    for (int i = 0; i < n; ++i) MRB_REQUIRE(s.x[i], "scalar_combine: null scalar %d", i);
+    k_scalar_combine<<<1, 32, 0, (cudaStream_t)stream_>>>(s, out);
+    return check_launch("scalar_combine");
+}
+
+extern "C" int mrb_scalar_scatter(const float* g, const float* w_host, int n, float* out, void* stream_) {
+    MRB_REQUIRE(g && out, "scalar_scatter: null pointer");
+    ScalarSet s;
+    if (int rc = fill_scalar_set(s, nullptr, w_host, n, "scalar_scatter")) return rc;
+    k_scalar_scatter<<<1, 32, 0, (cudaStream_t)stream_>>>(g, s, out);
+    return check_launch("scalar_scatter");
 }
 
 extern "C" int mrb_edge_loss_fwd(const float* pos, const long long* adj, long long E, double* acc, float* out,

@@ -1117,6 +1117,95 @@ def chamfer_knn(p: Tensor, q: Tensor, k: int = 0):
     return _Chamfer.apply(p, q, int(k))
 
 
+class _ChamferTotal(torch.autograd.Function):
+    """scale * (sum_i min_j |p_i - q_j|^2 + sum_j min_i |p_i - q_j|^2) as ONE scalar (what mesh_loss needs,
+    loss_functions.py:62-66) + the index outputs: the two nearest-neighbour distance arrays live in one buffer, so the sum,
+    the add and the division by point_cloud_size are a single reduction launch, and the backward is one kernel."""
+
+    @staticmethod
+    def forward(ctx, p, q, k, scale):
+        _require_cuda(p, "chamfer")
+        _require_cuda(q, "chamfer")
+        pc, qc = _f32c(p), _f32c(q)
+        B, P, _ = pc.shape
+        Q = qc.shape[1]
+        dev = p.device
+        d = torch.empty(B * (P + Q), dtype=torch.float32, device=dev)
+        ip = torch.empty(B, P, dtype=torch.int32, device=dev)
+        iq = torch.empty(B, Q, dtype=torch.int32, device=dev)
+        kp = torch.empty(B, P, k, dtype=torch.int32, device=dev) if k else None
+        kq = torch.empty(B, Q, k, dtype=torch.int32, device=dev) if k else None
+        ws = torch.empty(_lib.load().mrb_knn_workspace_bytes(B, P, Q), dtype=torch.uint8, device=dev)
+        _lib.call("mrb_knn_fwd", _lib.ptr(pc.detach()), _lib.ptr(qc.detach()), B, P, Q, k, d.data_ptr(), _lib.ptr(ip), _lib.ptr(kp),
+                  d.data_ptr() + 4 * B * P, _lib.ptr(iq), _lib.ptr(kq), _lib.ptr(ws))
+        acc = torch.empty(1, dtype=torch.float64, device=dev)
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        _lib.call("mrb_sum_scaled", _lib.ptr(d), B * (P + Q), float(scale), _lib.ptr(acc), _lib.ptr(out))
+        ctx.save_for_backward(pc, qc, ip, iq)
+        ctx.scale = float(scale)
+        ctx.mark_non_differentiable(ip, iq)
+        if k:
+            ctx.mark_non_differentiable(kp, kq)
+        return out[0], ip, iq, kp, kq
+
+    @staticmethod
+    def backward(ctx, g, *_):
+        pc, qc, ip, iq = ctx.saved_tensors
+        B, P, _ = pc.shape
+        Q = qc.shape[1]
+        gp = torch.zeros_like(pc) if ctx.needs_input_grad[0] else None
+        gq = torch.zeros_like(qc) if ctx.needs_input_grad[1] else None
+        gs = _lib.ptr(_f32c(g).reshape(1))
+        _lib.call("mrb_chamfer_bwd", _lib.ptr(pc), _lib.ptr(qc), B, P, Q, _lib.ptr(ip), _lib.ptr(iq), gs, gs, ctx.scale,
+                  _lib.ptr(gp), _lib.ptr(gq))
+        return gp, gq, None, None
+
+
+def chamfer_total(p: Tensor, q: Tensor, k: int, scale: float):
+    """(scale * (loss_1 + loss_2), idx_p, idx_q, knn_p, knn_q) -- see ``_ChamferTotal``."""
+    return _ChamferTotal.apply(p, q, int(k), float(scale))
+
+
+class _ScalarCombine(torch.autograd.Function):
+    """sum_i w_i * x_i over 0-dim CUDA tensors in one launch (backward: one launch for all the g * w_i)."""
+
+    @staticmethod
+    def forward(ctx, weights, *xs):
+        n = len(xs)
+        xc = [_f32c(x.detach()).reshape(1) for x in xs]
+        _require_cuda(xc[0], "weighted scalar sum")
+        out = torch.empty(1, dtype=torch.float32, device=xc[0].device)
+        ptrs = (ctypes.c_void_p * n)(*[x.data_ptr() for x in xc])
+        w = (ctypes.c_float * n)(*[float(v) for v in weights])
+        _lib.call("mrb_scalar_combine", ptrs, w, n, _lib.ptr(out))
+        ctx.weights = tuple(float(v) for v in weights)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        n = len(ctx.weights)
+        if all(v == 1.0 for v in ctx.weights):
+            return (None,) + (g,) * n                       # a plain sum: every term receives g itself, no kernel
+        out = torch.empty(n, dtype=torch.float32, device=g.device)
+        w = (ctypes.c_float * n)(*ctx.weights)
+        _lib.call("mrb_scalar_scatter", _lib.ptr(_f32c(g).reshape(1)), w, n, _lib.ptr(out))
+        return (None,) + tuple(out[i] for i in range(n))
+
+
+def weighted_scalar_sum(xs: Sequence[Tensor], weights: Optional[Sequence[float]] = None) -> Tensor:
+    """``sum(w * x for w, x in zip(weights, xs))`` for 0-dim CUDA tensors (loss terms) as one kernel; weights default to 1."""
+    xs = list(xs)
+    if len(xs) == 1 and (weights is None or float(weights[0]) == 1.0):
+        return xs[0]
+    if len(xs) > 16 or not all(isinstance(x, Tensor) and x.is_cuda for x in xs):
+        total = None
+        for i, x in enumerate(xs):
+            t = x if weights is None else x * float(weights[i])
+            total = t if total is None else total + t
+        return total
+    return _ScalarCombine.apply(tuple([1.0] * len(xs) if weights is None else weights), *xs)
+
+
 class _NormalLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, p, q, knn_p, knn_q, idx_p, idx_q):
@@ -1163,6 +1252,59 @@ class _NormalLoss(torch.autograd.Function):
             gq = torch.zeros_like(qc)
             _lib.call("mrb_normals_bwd", _lib.ptr(qc), _lib.ptr(knn_q), B, Q, k, _lib.ptr(gnq), _lib.ptr(gq))
         return gp, gq, None, None, None, None
+
+
+class _NormalLossTotal(torch.autograd.Function):
+    """scale * (sum_i |n_p[i] . n_q[idx_p[i]]| + sum_j |n_q[j] . n_p[idx_q[j]]|) as one scalar (loss_functions.py:69-72 with
+    the negation and the division folded into ``scale``)."""
+
+    @staticmethod
+    def forward(ctx, p, q, knn_p, knn_q, idx_p, idx_q, scale):
+        _require_cuda(p, "normal loss")
+        pc, qc = _f32c(p), _f32c(q)
+        B, P, _ = pc.shape
+        Q = qc.shape[1]
+        if P != Q:
+            raise RuntimeError("normal loss requires equally sized clouds (reference semantics)")
+        k = knn_p.shape[2]
+        dev = p.device
+        i32 = lambda t: t if (t.dtype == torch.int32 and t.is_contiguous()) else t.to(torch.int32).contiguous()
+        knn_p, knn_q, idx_p, idx_q = i32(knn_p), i32(knn_q), i32(idx_p), i32(idx_q)
+        n_p = torch.empty(B, P, 3, dtype=torch.float32, device=dev)
+        n_q = torch.empty(B, Q, 3, dtype=torch.float32, device=dev)
+        _lib.call("mrb_normals_fwd", _lib.ptr(pc), _lib.ptr(knn_p), B, P, k, _lib.ptr(n_p))
+        _lib.call("mrb_normals_fwd", _lib.ptr(qc), _lib.ptr(knn_q), B, Q, k, _lib.ptr(n_q))
+        acc = torch.empty(2, dtype=torch.float64, device=dev)
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        _lib.call("mrb_normal_loss_total_fwd", _lib.ptr(n_p), _lib.ptr(n_q), B, P, Q, _lib.ptr(idx_p), _lib.ptr(idx_q), float(scale),
+                  _lib.ptr(acc), _lib.ptr(out))
+        ctx.save_for_backward(pc, qc, knn_p, knn_q, idx_p, idx_q, n_p, n_q)
+        ctx.scale = float(scale)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        pc, qc, knn_p, knn_q, idx_p, idx_q, n_p, n_q = ctx.saved_tensors
+        B, P, _ = pc.shape
+        Q = qc.shape[1]
+        k = knn_p.shape[2]
+        need_p, need_q = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gnp = torch.zeros_like(n_p) if need_p else None
+        gnq = torch.zeros_like(n_q) if need_q else None
+        _lib.call("mrb_normal_loss_total_bwd", _lib.ptr(n_p), _lib.ptr(n_q), B, P, Q, _lib.ptr(idx_p), _lib.ptr(idx_q),
+                  _lib.ptr(_f32c(g).reshape(1)), ctx.scale, _lib.ptr(gnp), _lib.ptr(gnq))
+        gp = gq = None
+        if need_p:
+            gp = torch.zeros_like(pc)
+            _lib.call("mrb_normals_bwd", _lib.ptr(pc), _lib.ptr(knn_p), B, P, k, _lib.ptr(gnp), _lib.ptr(gp))
+        if need_q:
+            gq = torch.zeros_like(qc)
+            _lib.call("mrb_normals_bwd", _lib.ptr(qc), _lib.ptr(knn_q), B, Q, k, _lib.ptr(gnq), _lib.ptr(gq))
+        return gp, gq, None, None, None, None, None
+
+
+def normal_total(p: Tensor, q: Tensor, knn_p: Tensor, knn_q: Tensor, idx_p: Tensor, idx_q: Tensor, scale: float) -> Tensor:
+    return _NormalLossTotal.apply(p, q, knn_p, knn_q, idx_p, idx_q, float(scale))
 
 
 def normal_distance(p: Tensor, q: Tensor, knn_p: Tensor, knn_q: Tensor, idx_p: Tensor, idx_q: Tensor):

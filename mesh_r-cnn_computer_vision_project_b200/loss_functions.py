@@ -35,15 +35,11 @@ def batched_mesh_loss(vertex_positions_pred: List[Tensor], mesh_faces_pred: Tens
                       randomness=None) -> Tuple[Tensor, Tensor, Tensor]:
     """Sum over the refinement stages of (chamfer, normal, edge) -- reference loss_functions.py:17-35.
     ``randomness``: optional list (one entry per stage) of ``(rnd_pred, rnd_gt)`` injected draws, see ``mesh_loss``."""
-    chamfer = normal = edge = None
-    for s, pos in enumerate(vertex_positions_pred):
-        c, n, e = mesh_loss(pos, mesh_faces_pred, pred_adjacency, vertices_per_sample_pred, faces_per_sample_pred,
-                            batch, point_cloud_size, num_neighbours_for_normal_loss,
-                            randomness=None if randomness is None else randomness[s])
-        chamfer = c if chamfer is None else chamfer + c
-        normal = n if normal is None else normal + n
-        edge = e if edge is None else edge + e
-    return chamfer, normal, edge
+    terms = [mesh_loss(pos, mesh_faces_pred, pred_adjacency, vertices_per_sample_pred, faces_per_sample_pred, batch,
+                       point_cloud_size, num_neighbours_for_normal_loss,
+                       randomness=None if randomness is None else randomness[s])
+             for s, pos in enumerate(vertex_positions_pred)]
+    return tuple(F_.weighted_scalar_sum([t[i] for t in terms]) for i in range(3))     # one launch per term (was 2 adds each)
 
 
 def mesh_loss(vertex_positions_pred: Tensor, mesh_faces_pred: Tensor, pred_adjacency: Tensor,
@@ -68,11 +64,9 @@ def mesh_loss(vertex_positions_pred: Tensor, mesh_faces_pred: Tensor, pred_adjac
     # computed once per batch object (device-resident cache, functional.cached_face_cdf)
     cloud_gt, _ = F_.sample_points(pos_gt, faces_gt, batch.vertice_index, batch.face_index, n, cdf_owner=batch, **rnd_gt)
 
-    loss_p, loss_gt, idx_p, idx_gt, knn_p, knn_gt = F_.chamfer_knn(cloud_pred, cloud_gt, k)         # :62-65,141
-    chamfer_loss = (loss_p + loss_gt) / point_cloud_size                                            # :66
-
-    nd_p, nd_gt = F_.normal_distance(cloud_pred, cloud_gt, knn_p, knn_gt, idx_p, idx_gt)            # :69-71
-    normal_loss = -(nd_p + nd_gt) / point_cloud_size                                                # :72
+    # :62-66,141  (loss_p + loss_gt) / point_cloud_size as one scalar; :69-72  -(nd_p + nd_gt) / point_cloud_size likewise
+    chamfer_loss, idx_p, idx_gt, knn_p, knn_gt = F_.chamfer_total(cloud_pred, cloud_gt, k, 1.0 / point_cloud_size)
+    normal_loss = F_.normal_total(cloud_pred, cloud_gt, knn_p, knn_gt, idx_p, idx_gt, -1.0 / point_cloud_size)
     return chamfer_loss, normal_loss, edge_loss
 
 

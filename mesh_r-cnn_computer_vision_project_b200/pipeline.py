@@ -100,9 +100,8 @@ class RefinementHead(nn.Module):
                 for t in terms:
                     for x in t:
                         x.record_stream(main)
-                chamfer, normal, edge = terms[0]
-                for c, n, e in terms[1:]:
-                    chamfer, normal, edge = chamfer + c, normal + n, edge + e
+                from . import functional as F_
+                chamfer, normal, edge = (F_.weighted_scalar_sum([t[i] for t in terms]) for i in range(3))
             else:
                 chamfer, normal, edge = batched_mesh_loss(positions[1:], faces, adj_index, vertice_index, face_index,
                                                           targets, randomness=loss_randomness)
@@ -119,8 +118,8 @@ LOSS_WEIGHTS = {"chamfer_loss": 1.0, "normal_loss": 0.1, "edge_loss": 0.5}
 
 def weighted_loss(losses: dict, weights: dict = LOSS_WEIGHTS) -> Tensor:
     """Weighted sum of the loss dict (reference utils/train_utils.py:208-225)."""
-    total = None
-    for k, w in weights.items():
-        if k in losses:
-            total = losses[k] * w if total is None else total + losses[k] * w
-    return total
+    from . import functional as F_
+    keys = [k for k in weights if k in losses]
+    if not keys:
+        return None
+    return F_.weighted_scalar_sum([losses[k] for k in keys], [weights[k] for k in keys])

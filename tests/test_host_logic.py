@@ -49,14 +49,18 @@ def test_flat_grad_bucket_survives_zero_grad_set_to_none():
     bucket.zero()                                                       # re-binds
     lin(x).pow(2).sum().backward()
     assert torch.allclose(bucket.flat, want)
-    # staged buckets: hooks count the parameters of a group; without a process group finish() is a no-op exchange
+    # staged buckets: gradients start as None (no accumulate kernels), hooks count the parameters of a group; without a
+    # process group nothing is packed or exchanged and the gradients stay where autograd put them
     sb = StagedGradBuckets([list(lin[0].parameters()), list(lin[1].parameters())])
+    assert all(p.grad is None for p in lin.parameters())
     lin(x).pow(2).sum().backward()
     assert sb._pending == [0, 0] and sb._issued == [True, True]
     sb.finish()
-    assert torch.allclose(torch.cat([b.flat for b in sb.buckets]), want)
+    assert torch.allclose(torch.cat([p.grad.flatten() for p in lin.parameters()]), want)
+    sb._pack(0); sb._pack(1)                                             # what a multi-GPU run does before its all-reduce
+    assert torch.allclose(torch.cat(sb.flats), want)
     sb.zero()
-    assert sb._pending == [1, 1] and sb._issued == [False, False]
+    assert sb._pending == [1, 1] and sb._issued == [False, False] and lin[0].weight.grad is None
 
 
 def test_synthetic_inputs_are_deterministic_and_sized():
