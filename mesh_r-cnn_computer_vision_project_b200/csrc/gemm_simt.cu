@@ -173,19 +173,27 @@ __global__ void __launch_bounds__(256) k_skinny_tn(int M, int N, int K, const fl
     for (int m = 0; m < MACC; ++m)
 #pragma unroll
         for (int j = 0; j < JMAX; ++j) acc[m][j] = 0.f;
-    for (int k = k0 + warp_id(); k < k1; k += 8) {
-        float a[MACC];
+    // two rows of the chunk per iteration: their loads are all issued before the first FMA (the loop is latency bound: a
+    // warp owns only ~10 rows)
+    for (int k = k0 + warp_id(); k < k1; k += 16) {
+        const int kb = min(k + 8, k1 - 1);
+        const bool has_b = k + 8 < k1;
+        float a[MACC], a2[MACC], b[JMAX], b2[JMAX];
 #pragma unroll
-        for (int m = 0; m < MACC; ++m) a[m] = (m < M) ? __ldg(A + (size_t)k * lda + m) : 0.f;
+        for (int m = 0; m < MACC; ++m) {
+            a[m] = (m < M) ? __ldg(A + (size_t)k * lda + m) : 0.f;
+            a2[m] = (m < M && has_b) ? __ldg(A + (size_t)kb * lda + m) : 0.f;
+        }
 #pragma unroll
         for (int j = 0; j < JMAX; ++j) {
             const int n = j * 32 + lane_id();
-            if (n < N) {
-                const float b = B[(size_t)k * ldb + n];
-#pragma unroll
-                for (int m = 0; m < MACC; ++m) acc[m][j] = fmaf(a[m], b, acc[m][j]);
-            }
+            b[j] = (n < N) ? __ldg(B + (size_t)k * ldb + n) : 0.f;
+            b2[j] = (n < N) ? __ldg(B + (size_t)kb * ldb + n) : 0.f;
         }
+#pragma unroll
+        for (int j = 0; j < JMAX; ++j)
+#pragma unroll
+            for (int m = 0; m < MACC; ++m) acc[m][j] = fmaf(a2[m], b2[j], fmaf(a[m], b[j], acc[m][j]));
     }
 #pragma unroll
     for (int m = 0; m < MACC; ++m) {
