@@ -354,16 +354,34 @@ def kernel_rooflines(breakdown, stats, peaks, fma_peak, widths):
         byts = 2 * 4 * SV * 128 + 4 * (E + SV + 1)            # SURVEY 8d compulsory bytes
         roof["mrb_csr_gather_fwd"] = {"bound": "hbm", "achieved": round(byts / t / 1e9, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                       "frac": round(byts / t / 1e9 / peaks["hbm_gbs"], 4)}
-    if "mrb_gemm_tc" in breakdown and widths:
-        ms = breakdown["mrb_gemm_tc"]["ms_per_step"] * 1e-3
-        flops = sum(2.0 * SV * k * 256 for k in widths) * 2                  # fwd + dgrad
-        byts = sum(4.0 * SV * (k + 256) for k in widths) * 2                 # A read + C written once
+    if "mrb_gemm_tc_acc" in breakdown and "mrb_gemm_tc" in breakdown and widths:
+        # split-input GraphConv: forward projections x @ [W0x | W1x] (mrb_gemm_tc_acc) and input gradients gy @ [W0x | W1x]^T
+        # (mrb_gemm_tc); `widths` = (rows M, K, N) of every call of one step
+        ms = (breakdown["mrb_gemm_tc_acc"]["ms_per_step"] + breakdown["mrb_gemm_tc"]["ms_per_step"]) * 1e-3
+        flops = sum(2.0 * m * k * n for m, k, n in widths)
+        byts = sum(4.0 * m * (k + n) for m, k, n in widths)
         tf32_peak = peaks.get("bf16_tflops", 2250.0) / 2.0
-        roof["mrb_gemm_tc"] = {"bound": "tensor", "achieved": round(3 * flops / ms / 1e12, 1), "peak": round(tf32_peak, 1),
-                               "unit": "TFLOP/s (TF32 issued, 3xTF32; peak = measured bf16 peak / 2)",
-                               "frac": round(3 * flops / ms / 1e12 / tf32_peak, 4),
-                               "tensor_tflops_fp32_equiv": round(flops / ms / 1e12, 1),
-                               "hbm_gbs": round(byts / ms / 1e9, 1), "hbm_frac": round(byts / ms / 1e9 / peaks["hbm_gbs"], 4)}
+        roof["tcgen05 projections (mrb_gemm_tc_acc + mrb_gemm_tc)"] = {
+            "bound": "tensor", "achieved": round(3 * flops / ms / 1e12, 1), "peak": round(tf32_peak, 1),
+            "unit": "TFLOP/s (TF32 issued, 3xTF32; peak = measured bf16 peak / 2)",
+            "frac": round(3 * flops / ms / 1e12 / tf32_peak, 4), "tensor_tflops_fp32_equiv": round(flops / ms / 1e12, 1),
+            "hbm_gbs": round(byts / ms / 1e9, 1), "hbm_frac": round(byts / ms / 1e9 / peaks["hbm_gbs"], 4),
+            "calls_per_step": len(widths)}
+    if "mrb_gemm_tc_wgrad_split" in breakdown:
+        ms = breakdown["mrb_gemm_tc_wgrad_split"]["ms_per_step"] * 1e-3
+        calls = breakdown["mrb_gemm_tc_wgrad_split"]["calls_per_step"]
+        flops = calls * 2.0 * SV * 128 * 256
+        byts = calls * 4.0 * SV * (128 + 256)
+        tf32_peak = peaks.get("bf16_tflops", 2250.0) / 2.0
+        roof["mrb_gemm_tc_wgrad_split"] = {"bound": "tensor", "achieved": round(3 * flops / ms / 1e12, 1), "peak": round(tf32_peak, 1),
+                                           "unit": "TFLOP/s (TF32 issued)", "frac": round(3 * flops / ms / 1e12 / tf32_peak, 4),
+                                           "hbm_gbs": round(byts / ms / 1e9, 1), "hbm_frac": round(byts / ms / 1e9 / peaks["hbm_gbs"], 4)}
+    if "mrb_gc_gather_fwd" in breakdown:
+        t = per_call("mrb_gc_gather_fwd")
+        byts = 3 * 4 * SV * 128 + 4 * (E + SV + 1)            # self + neighbour matrix read once + output
+        roof["mrb_gc_gather_fwd"] = {"bound": "hbm", "achieved": round(byts / t / 1e9, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                     "frac": round(byts / t / 1e9 / peaks["hbm_gbs"], 4),
+                                     "note": "per-call average over the y-only, +position and +texel variants of one step"}
     if "mrb_cubify_emit" in breakdown:
         t = (breakdown["mrb_cubify_emit"]["ms_per_step"] + breakdown["mrb_cubify_count"]["ms_per_step"]) * 1e-3
         byts = 4 * B * stats["grid"] ** 3 + 12 * SV + 24 * SF + 16 * E + 16 * B
@@ -576,7 +594,7 @@ def run_cuda(args):
     #  * every timing event is created and recorded once now and reused afterwards (EventPool);
     #  * the first ~12 steps of a fresh process ramp from 7.4 to 6.3 ms (clocks, allocator growth): the same step is run
     #    untimed for STARTUP_SECONDS before the W warm-up steps.  Both are start-up cost, not steady-state throughput.
-    pool = EventPool(2 * steps + 64)
+    pool = EventPool(2 * steps + 72)
     t_start = time.perf_counter()
     startup_steps = 0
     while time.perf_counter() - t_start < STARTUP_SECONDS:
@@ -595,6 +613,22 @@ def run_cuda(args):
     sync_all()
     gc.collect()
     gc.disable()            # no cyclic-GC pause inside a timed step (autograd graphs are freed by refcount)
+    # settle (untimed, collective-free, bounded): the timed region starts once 5 consecutive steps run within 5 % of the fastest
+    # step seen so far -- a disturbed box (another tenant's burst, a slow NVML query) otherwise lands in the first timed steps
+    settle_ev = pool.take(2)
+    best, streak, settle_steps = float("inf"), 0, 0
+    while settle_steps < 120 and streak < 5:
+        settle_ev[0][0].record()
+        wl.step(exchange=False)
+        settle_ev[0][1].record()
+        torch.cuda.synchronize()
+        t_ms = settle_ev[0][0].elapsed_time(settle_ev[0][1])
+        best = min(best, t_ms)
+        streak = streak + 1 if t_ms <= 1.05 * best else 0
+        settle_steps += 1
+    for _ in range(2):
+        wl.step()           # back to the pipelined, collective-carrying rhythm (every rank runs exactly these two)
+    sync_all()
 
     # ---- timed region 1: inputs resident in HBM ----------------------------------------------------------------
     res_ms, launches = timed_resident(wl, pool, steps, flush, sync_all)
@@ -616,7 +650,11 @@ def run_cuda(args):
     fma_peak = measure_fma_peak(dev)
     if rank == 0:
         breakdown = instrumented_breakdown(wl, reps=2)
-        roof_all = kernel_rooflines(breakdown, stats, peaks, fma_peak, [259, 131, 131, 387, 131, 131, 387, 131, 131])
+        SVn, R = stats["SV"], stats["B"] * 144
+        # one headline step: 8 GraphConvs with a dense 128-wide block (stage 0's graphConv0 has none) forward + input gradient,
+        # 3 texel projections (4 608 texels x 256 channels -> 256) forward + their gradient
+        widths = [(SVn, 128, 256)] * 8 + [(SVn, 256, 128)] * 8 + [(R, 256, 256)] * 6
+        roof_all = kernel_rooflines(breakdown, stats, peaks, fma_peak, widths)
         top = next(iter(breakdown))
         if top == "mrb_knn_fwd":
             r = roof_all[top]
@@ -663,8 +701,9 @@ def run_cuda(args):
                        "parallelism": "mesh-sharded dp%d (meshes dealt by occupied-voxel count), NCCL grad all-reduce(SUM) per stage "
                                       "bucket from backward hooks" % world,
                        "per_gpu": stats, "l2": "256 MiB flush write between timed iterations",
-                       "startup": "%d untimed steps (%.0f s) + pre-recorded timing-event pool, before the W warm-up steps; "
-                                  "%d untimed e2e steps before the e2e region" % (startup_steps, STARTUP_SECONDS, max(warmup, E2E_WARMUP_MIN)),
+                       "startup": "%d untimed steps (%.0f s) + pre-recorded timing-event pool, before the W warm-up steps; %d settle "
+                                  "steps (until 5 in a row within 5 %% of the fastest); %d untimed e2e steps before the e2e region"
+                                  % (startup_steps, STARTUP_SECONDS, settle_steps, max(warmup, E2E_WARMUP_MIN)),
                        "optimizer": "none (metric is fwd+bwd)"},
             "e2e": {"value": round(total_meshes / (e2e_total * 1e-3), 2), "unit": "meshes/s",
                     "h2d_bytes_per_step": wl_h2d_bytes(B), "d2h_bytes_per_step": 12,
