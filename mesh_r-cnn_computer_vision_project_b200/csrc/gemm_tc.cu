@@ -141,6 +141,15 @@ constexpr int TC_SINGLE_ACC_CHUNKS = MRB_TC_SINGLE_ACC_CHUNKS;   // K <= 512: on
 constexpr int TC_SMEM_LIMIT = 232448;                                    // 227 KB opt-in maximum per CTA
 constexpr int TC_RING_BYTES = TC_SMEM_LIMIT - EPI_BYTES - 1024 - 256;   // what the stage ring may use
 
+#ifdef MRB_TC_TIMELINE
+// Diagnostic build only (scripts/gemm_timeline.sh): per-role clock64() stamps of CTA 0.
+__device__ long long g_tl[4][2048];
+__device__ int g_tl_n[4];
+#define TL(role, tag) do { if (blockIdx.x == 0 && tl_n < 2048) { g_tl[role][tl_n++] = (clock64() << 8) | (tag); g_tl_n[role] = tl_n; } } while (0)
+#else
+#define TL(role, tag) do { } while (0)
+#endif
+
 // Persistent: grid = min(#tiles, #SMs); every role loops over the CTA's tiles with pipeline state that carries across
 // tiles, so global-load latency, tensor work and the C write-back of consecutive tiles overlap on one SM.
 __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
@@ -158,6 +167,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * TC_MAX_STAGES + 2 + a); };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef MRB_TC_TIMELINE
+    int tl_n = 0;
+#endif
     const int NT = p.NT;
     const int b_bytes = NT * BK * 4;     // one (hi | lo) weight tile
     const int total_tiles = p.mtiles * p.ntiles;
@@ -226,6 +238,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
                     if (it < total_its) {
                         const int s = it % STAGES, use = it / STAGES;
                         if (use > 0) mbar_wait(empty_bar(s), (use - 1) & 1);
+                        if (threadIdx.x == 0) TL(0, 50);
                         unsigned char* a_hi = smem + s * STAGE_BYTES;
                         unsigned char* a_lo = a_hi + A_BYTES;
                         const int m0 = ((blockIdx.x + (it / p.nchunks) * gridDim.x) / p.ntiles) * BM;
@@ -250,6 +263,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         __syncwarp();
                         if (lane == 0) mbar_arrive(full_bar(s));
+                        if (threadIdx.x == 0) TL(0, 51);
                         if (it + PREFETCH < total_its) load_it(it + PREFETCH, v[d]);
                     }
                 }
@@ -315,6 +329,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
             const int ab = j % p.acc_bufs, use = j / p.acc_bufs;
             const int m0 = (tile / p.ntiles) * BM, n0 = (tile % p.ntiles) * NT;
             mbar_wait(tfull_bar(ab), use & 1);
+            if (warp == PROD_WARPS && lane == 0) TL(1, 40);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tmem_d = tmem_base + (uint32_t)(ab * acc_cols);
             const int gm_mine = m0 + ew * 32 + lane;
@@ -328,6 +343,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
                     tmem_ld32(taddr, v0);
                     if (p.nacc > 1) tmem_ld32(taddr + (uint32_t)p.tmem_cols, v1);   // main + cross-term accumulator
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (warp == PROD_WARPS && lane == 0) TL(1, 43);
                     if (p.nacc > 1) {
 #pragma unroll
                         for (int q = 0; q < 32; ++q) acc[q] = __uint_as_float(v0[q]) + __uint_as_float(v1[q]);
@@ -347,6 +363,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty_bar(ab));
+                    if (warp == PROD_WARPS && lane == 0) TL(1, 41);
                 }
                 const int colbase = n0 + c0;
                 if (aligned && c0 + 32 <= NT && colbase + 32 <= p.N) {
@@ -359,6 +376,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
                     for (int q = 0; q < 8; ++q)
                         st4[lane * 8 + (q ^ (lane & 7))] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
                     __syncwarp();
+                    if (warp == PROD_WARPS && lane == 0) TL(1, 44);
                     const int rsub = lane >> 3, ch = lane & 7;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -377,6 +395,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
                             *dst = o;
                         }
                     }
+                    if (warp == PROD_WARPS && lane == 0) TL(1, 45);
                 } else {
                     __syncwarp();
 #pragma unroll
@@ -393,6 +412,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
                     __syncwarp();
                 }
             }
+            if (warp == PROD_WARPS && lane == 0) TL(1, 42);
             if (blk_beg >= blk_end) {                 // this half has no column block (NT <= 32): still release the buffer
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
@@ -411,9 +431,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
                 const uint32_t tmem_d = tmem_base + (uint32_t)(ab * acc_cols);
+                TL(2, 10);
                 for (int c = 0; c < p.nchunks; ++c, ++it) {
                     const int s = it % STAGES, suse = it / STAGES;
                     mbar_wait(full_bar(s), suse & 1);
+                    TL(2, 20);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_BYTES;
                     const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + b_bytes;
@@ -439,6 +461,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
 #endif
                     }
                     umma_commit(empty_bar(s));                 // stage reusable once these MMAs retire
+                    TL(2, 21);
                 }
                 umma_commit(tfull_bar(ab));                    // accumulator complete -> epilogue
             }
@@ -453,6 +476,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
                 for (int c = 0; c < p.nchunks; ++c, ++it) {
                     const int s = it % STAGES, use = it / STAGES;
                     if (use > 0) mbar_wait(empty_bar(s), (use - 1) & 1);
+                    TL(3, 60);
                     const uint32_t dst = smem_base + s * STAGE_BYTES + 2 * A_BYTES;
                     mbar_expect_tx(full_bar(s), 2 * b_bytes);
                     bulk_g2s(dst, img + (size_t)c * 2 * b_bytes, b_bytes, full_bar(s));
@@ -774,6 +798,16 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tn(ParamsTN p) {
 
 using namespace mrb;
 using namespace mrb::gemmtc;
+
+#ifdef MRB_TC_TIMELINE
+extern "C" int mrb_debug_tc_timeline(long long* stamps, int* counts, int reset) {
+    if (reset) { int z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(g_tl_n, z, sizeof(z)); return 0; }
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(stamps, g_tl, sizeof(long long) * 4 * 2048);
+    cudaMemcpyFromSymbol(counts, g_tl_n, sizeof(int) * 4);
+    return 0;
+}
+#endif
 
 extern "C" long long mrb_gemm_tc_image_bytes(int K, int N) {
     if (K <= 0 || N <= 0) return -1;

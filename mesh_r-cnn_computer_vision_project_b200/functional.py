@@ -94,12 +94,15 @@ class _VoxelBCE(torch.autograd.Function):
                   _lib.ptr(out))
         ctx.save_for_backward(xc, tc)
         ctx.from_logits = bool(from_logits)
+        ctx.set_materialize_grads(False)        # no zero-filled "gradient" of the probabilities
         if probs is not None:
             ctx.mark_non_differentiable(probs)
         return out[0], probs
 
     @staticmethod
     def backward(ctx, g, _gprobs):
+        if g is None:
+            return None, None, None, None
         xc, tc = ctx.saved_tensors
         gx = torch.empty_like(xc)
         _lib.call("mrb_voxel_bce_bwd", _lib.ptr(xc), _lib.ptr(tc), xc.numel(), int(ctx.from_logits), _lib.ptr(_f32c(g).reshape(1)),
@@ -970,11 +973,14 @@ class _Sample(torch.autograd.Function):
                   _lib.ptr(w), _lib.ptr(cloud), _lib.ptr(stats))
         ctx.save_for_backward(cloud, stats, fidx, w, f, v_off)
         ctx.dims = (B, n, tuple(v.shape))
+        ctx.set_materialize_grads(False)        # autograd would otherwise zero-fill an int "gradient" for fidx every backward
         ctx.mark_non_differentiable(fidx)
         return cloud, fidx
 
     @staticmethod
     def backward(ctx, gcloud, _gfidx):
+        if gcloud is None:
+            return (None,) * 13
         cloud, stats, fidx, w, f, v_off = ctx.saved_tensors
         B, n, vshape = ctx.dims
         gverts = torch.zeros(vshape, dtype=torch.float32, device=cloud.device)
@@ -1090,6 +1096,7 @@ class _Chamfer(torch.autograd.Function):
         _lib.call("mrb_sum_scaled", _lib.ptr(dq), B * Q, 1.0, _lib.ptr(acc) + 8, _lib.ptr(sums) + 4)
         ctx.save_for_backward(pc, qc, ip, iq)
         outs = [sums[0], sums[1], ip, iq]
+        ctx.set_materialize_grads(False)        # no zero-filled int "gradients" for the index outputs
         ctx.mark_non_differentiable(ip, iq)
         if k:
             ctx.mark_non_differentiable(kp, kq)
@@ -1100,6 +1107,8 @@ class _Chamfer(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g1, g2, *_):
+        if g1 is None and g2 is None:
+            return None, None, None
         pc, qc, ip, iq = ctx.saved_tensors
         B, P, _ = pc.shape
         Q = qc.shape[1]
@@ -1143,6 +1152,7 @@ class _ChamferTotal(torch.autograd.Function):
         _lib.call("mrb_sum_scaled", _lib.ptr(d), B * (P + Q), float(scale), _lib.ptr(acc), _lib.ptr(out))
         ctx.save_for_backward(pc, qc, ip, iq)
         ctx.scale = float(scale)
+        ctx.set_materialize_grads(False)        # no zero-filled int "gradients" for the four index outputs (4 fill launches)
         ctx.mark_non_differentiable(ip, iq)
         if k:
             ctx.mark_non_differentiable(kp, kq)
@@ -1150,6 +1160,8 @@ class _ChamferTotal(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g, *_):
+        if g is None:
+            return None, None, None, None
         pc, qc, ip, iq = ctx.saved_tensors
         B, P, _ = pc.shape
         Q = qc.shape[1]

@@ -24,7 +24,9 @@ else:
 for _ in range(4):
     run()
 torch.cuda.synchronize()
+torch.cuda.profiler.start()                 # `ncu --profile-from-start off`: forward AND backward (the autograd thread is outside the NVTX range)
 torch.cuda.nvtx.range_push("profiled")
 run()
 torch.cuda.synchronize()
 torch.cuda.nvtx.range_pop()
+torch.cuda.profiler.stop()
