@@ -598,7 +598,8 @@ constexpr int TN_TAIL_MAX = 4;
 constexpr int TN_PROD_WARPS = 8;                       // warp w stages vertices [4w, 4w+4) of every chunk = 16-byte k chunk w
 constexpr int TN_THREADS = (TN_PROD_WARPS + 1) * 32;   // producers (also the epilogue) | MMA issuer
 // NBMAX: 32-column blocks of G a producer thread stages (N <= 32 * NBMAX); PF: chunks in flight per producer thread.  The
-// register file allows two chunks in flight only for N <= 128 (16 + 4 * NBMAX staging registers per chunk, 168 per thread).
+// register file allows two chunks in flight only for N <= 128 (16 + 4 * NBMAX staging registers per chunk; 9 warps put 3 on
+// one scheduler, which caps a thread at 168 registers: <8, 2> spills 656 bytes and runs 2x slower, 119 vs 58 us at V = 50k).
 template <int NBMAX, int TN_PREFETCH>
 __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tn(ParamsTN p) {
     extern __shared__ unsigned char smem_raw[];
@@ -612,6 +613,12 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tn(ParamsTN p) {
     const uint32_t tfull_bar = bar_base + 8u * (2 * STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef MRB_TC_TIMELINE
+    int tl_n = 0;
+#define TLY(role, tag) do { if (blockIdx.y == 0) TL(role, tag); } while (0)
+#else
+#define TLY(role, tag) do { } while (0)
+#endif
     const int i0 = blockIdx.x * BM;
     const int NT = p.N;
     const int b_bytes = NT * BK * 4;
@@ -692,6 +699,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tn(ParamsTN p) {
                     if (c < nchunks) {
                         const int s = c % STAGES, use = c / STAGES;
                         if (use > 0) mbar_wait(empty_bar(s), (use - 1) & 1);
+                        if (threadIdx.x == 0) TLY(0, 50);
                         unsigned char* a_hi = smem + s * STAGE_BYTES;
                         unsigned char* a_lo = a_hi + A_BYTES;
                         unsigned char* b_hi = a_hi + 2 * A_BYTES;
@@ -706,6 +714,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tn(ParamsTN p) {
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         __syncwarp();
                         if (lane == 0) mbar_arrive(full_bar(s));
+                        if (threadIdx.x == 0) TLY(0, 51);
                         if (ntail) {
 #pragma unroll
                             for (int t = 0; t < 4; ++t)
@@ -723,7 +732,9 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tn(ParamsTN p) {
             }
             // ===== epilogue: TMEM -> registers -> vectorised fp32 reductions into C ========================================
             // warp w reads TMEM lane quadrant w % 4 (rows) and the column half w / 4
+            if (threadIdx.x == 0) TLY(0, 46);
             mbar_wait(tfull_bar, 0);
+            if (threadIdx.x == 0) TLY(0, 40);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int ew = warp & 3, half = warp >> 2;
             const int i = i0 + ew * 32 + lane;          // TMEM lane = row of the tile
@@ -743,6 +754,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tn(ParamsTN p) {
                                      : "memory");
                 }
             }
+            if (threadIdx.x == 0) TLY(0, 42);
             if (ntail) {
                 // all MMAs have retired (tfull), so the stage ring is free: sum the 8 warps' partial tail rows there
                 float* red = reinterpret_cast<float*>(smem);                   // [warp][m][256]
@@ -769,6 +781,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tn(ParamsTN p) {
             for (int c = 0; c < nchunks; ++c) {
                 const int s = c % STAGES, use = c / STAGES;
                 mbar_wait(full_bar(s), use & 1);
+                TLY(2, 20);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_hi = smem_base + s * STAGE_BYTES, a_lo = a_hi + A_BYTES;
                 const uint32_t b_hi = a_hi + 2 * A_BYTES, b_lo = b_hi + b_bytes;
@@ -924,6 +937,8 @@ static int launch_wgrad(const float* X, int ldx, const float* G, int ldg, int V,
     while (ceil_div(total_chunks, per_wave * waves) > 32) ++waves;
     p.chunks_per_split = max(1, ceil_div(total_chunks, per_wave * waves));
     const int splits = ceil_div(total_chunks, p.chunks_per_split);
+    // (splitting N = 256 into two 128-column CTAs so that <4, 2> keeps two chunks in flight was measured SLOWER -- 72 vs 59 us
+    //  at V = 50k, 247 vs 176 us at 206k: the cost is per chunk iteration, not per byte; profiles/r02/gemm_tn_timeline*.txt)
     if (N <= 128) k_gemm_tn<4, 2><<<dim3(mtiles, splits), TN_THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(p);
     else k_gemm_tn<8, 1><<<dim3(mtiles, splits), TN_THREADS, SMEM_BYTES, (cudaStream_t)stream_>>>(p);
     return check_launch(what);
