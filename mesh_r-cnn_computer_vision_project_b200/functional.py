@@ -1020,8 +1020,12 @@ def cached_face_cdf(owner, verts: Tensor, faces: Tensor, v_index: Sequence[int],
 
 
 def _next_seed() -> int:
-    # drawn from torch's CPU generator so that torch.manual_seed() makes sampling reproducible (no device sync)
-    return int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+    # drawn from torch's CPU generator so that torch.manual_seed() makes sampling reproducible (no device sync); the rank is
+    # mixed in, so ranks that were seeded identically still draw different surface samples for their shards
+    s = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        s ^= (torch.distributed.get_rank() * 0x9E3779B97F4A7C15) & (2 ** 62 - 1)
+    return s
 
 
 def sample_points(verts: Tensor, faces: Tensor, v_index: Sequence[int], f_index: Sequence[int], n: int,

@@ -184,6 +184,12 @@ assert g["vertex_positions"][0].shape == (9, 3) and float(g["vertex_positions"][
 assert g["edge_index"].tolist() == [[0, 4, 5, 8], [4, 0, 8, 5]], g["edge_index"].tolist()
 tot = all_reduce_losses({"chamfer_loss": torch.tensor(float(rank + 1)), "edge_loss": torch.tensor(2.0)})
 assert float(tot["chamfer_loss"]) == sum(range(1, world + 1)) and float(tot["edge_loss"]) == 2.0 * world
+# identically seeded ranks must still draw different surface-sampling seeds
+from meshrcnn_b200.functional import _next_seed
+torch.manual_seed(123)
+seeds = [None] * world
+dist.all_gather_object(seeds, _next_seed())
+assert len(set(seeds)) == world, seeds
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
