@@ -120,7 +120,9 @@ __global__ void __launch_bounds__(128) k_normals_fwd(const float* __restrict__ p
 
 // gn -> gpt (atomic scatter to the gathered rows):  n_j = V[0][j]
 //   K_ij = V[0][i] gn_j / (w_j - w_i) (i != j),  gS = V K V^T,  gY = Y (gS + gS^T)
-template <int KT>
+// PAD4: gpt rows are 4 floats wide (xyz + one unused lane), so a neighbour's three partial sums go out as ONE 16-byte
+// red.global.add.v4.f32 instead of three scalar atomics (the kernel is bound by the L2 atomic units: 30 -> 10 per point).
+template <int KT, bool PAD4>
 __global__ void __launch_bounds__(128) k_normals_bwd(const float* __restrict__ pt, const int32_t* __restrict__ knn, int P,
                                                      int k, const float* __restrict__ gn, float* __restrict__ gpt) {
     const int batch = blockIdx.y;
@@ -147,14 +149,23 @@ __global__ void __launch_bounds__(128) k_normals_bwd(const float* __restrict__ p
         for (int j = 0; j < 3; ++j) G[i][j] = T[i][0] * V[j][0] + T[i][1] * V[j][1] + T[i][2] * V[j][2];
     for (int i = 0; i < 3; ++i)
         for (int j = i; j < 3; ++j) { const double s = G[i][j] + G[j][i]; G[i][j] = s; G[j][i] = s; }
-    float* gb = gpt + (size_t)batch * P * 3;
+    float* gb = gpt + (size_t)batch * P * (PAD4 ? 4 : 3);
 #pragma unroll
     for (int j = 0; j < (KT > 0 ? KT : KMAX); ++j) {
         if (j >= (KT > 0 ? KT : k)) break;
-        const size_t r = 3 * (size_t)nn[j];
-        atomicAdd(gb + r, (float)(Y[j][0] * G[0][0] + Y[j][1] * G[1][0] + Y[j][2] * G[2][0]));
-        atomicAdd(gb + r + 1, (float)(Y[j][0] * G[0][1] + Y[j][1] * G[1][1] + Y[j][2] * G[2][1]));
-        atomicAdd(gb + r + 2, (float)(Y[j][0] * G[0][2] + Y[j][1] * G[1][2] + Y[j][2] * G[2][2]));
+        const float gx = (float)(Y[j][0] * G[0][0] + Y[j][1] * G[1][0] + Y[j][2] * G[2][0]);
+        const float gy = (float)(Y[j][0] * G[0][1] + Y[j][1] * G[1][1] + Y[j][2] * G[2][1]);
+        const float gz = (float)(Y[j][0] * G[0][2] + Y[j][1] * G[1][2] + Y[j][2] * G[2][2]);
+        if (PAD4) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gb + 4 * (size_t)nn[j]), "f"(gx), "f"(gy), "f"(gz),
+                         "f"(0.f)
+                         : "memory");
+        } else {
+            const size_t r = 3 * (size_t)nn[j];
+            atomicAdd(gb + r, gx);
+            atomicAdd(gb + r + 1, gy);
+            atomicAdd(gb + r + 2, gz);
+        }
     }
 }
 
@@ -274,15 +285,33 @@ extern "C" int mrb_normals_fwd(const float* pt, const int32_t* knn, int B, int P
     return check_launch("normals_fwd");
 }
 
-extern "C" int mrb_normals_bwd(const float* pt, const int32_t* knn, int B, int P, int k, const float* gn, float* gpt,
-                               void* stream_) {
+static int launch_normals_bwd(const float* pt, const int32_t* knn, int B, int P, int k, const float* gn, float* gpt, int ld_gpt,
+                              void* stream_) {
     MRB_REQUIRE(pt && knn && gn && gpt, "normals_bwd: null pointer");
     MRB_REQUIRE(k >= 1 && k <= KMAX, "normals_bwd: k must be in [1, %d]", KMAX);
+    MRB_REQUIRE(ld_gpt == 3 || (ld_gpt == 4 && ((uintptr_t)gpt & 15) == 0),
+                "normals_bwd: gradient rows must be 3 floats, or 4 floats and 16-byte aligned (got ld = %d)", ld_gpt);
     if (B == 0 || P == 0) return MRB_OK;
     const dim3 grid(ceil_div(P, 128), B);
-    if (k == 10) k_normals_bwd<10><<<grid, 128, 0, (cudaStream_t)stream_>>>(pt, knn, P, k, gn, gpt);
-    else k_normals_bwd<0><<<grid, 128, 0, (cudaStream_t)stream_>>>(pt, knn, P, k, gn, gpt);
+    cudaStream_t s = (cudaStream_t)stream_;
+    if (ld_gpt == 4) {
+        if (k == 10) k_normals_bwd<10, true><<<grid, 128, 0, s>>>(pt, knn, P, k, gn, gpt);
+        else k_normals_bwd<0, true><<<grid, 128, 0, s>>>(pt, knn, P, k, gn, gpt);
+    } else {
+        if (k == 10) k_normals_bwd<10, false><<<grid, 128, 0, s>>>(pt, knn, P, k, gn, gpt);
+        else k_normals_bwd<0, false><<<grid, 128, 0, s>>>(pt, knn, P, k, gn, gpt);
+    }
     return check_launch("normals_bwd");
+}
+
+extern "C" int mrb_normals_bwd(const float* pt, const int32_t* knn, int B, int P, int k, const float* gn, float* gpt,
+                               void* stream_) {
+    return launch_normals_bwd(pt, knn, B, P, k, gn, gpt, 3, stream_);
+}
+
+extern "C" int mrb_normals_bwd_ld(const float* pt, const int32_t* knn, int B, int P, int k, const float* gn, float* gpt,
+                                  int ld_gpt, void* stream_) {
+    return launch_normals_bwd(pt, knn, B, P, k, gn, gpt, ld_gpt, stream_);
 }
 
 extern "C" int mrb_normal_loss_fwd(const float* na, const float* nb, int B, int P, int Q, const int32_t* idx_a,

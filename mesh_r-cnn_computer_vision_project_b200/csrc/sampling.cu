@@ -317,6 +317,8 @@ __global__ void __launch_bounds__(256) k_sample_bwd_sums(const float* __restrict
     }
 }
 
+// PAD4: gverts rows are 4 floats wide (16-byte aligned), one red.global.add.v4.f32 per face corner instead of three atomics
+template <bool PAD4>
 __global__ void __launch_bounds__(256) k_sample_bwd(const float* __restrict__ gy, const float* __restrict__ y,
                                                     const double* __restrict__ stats, const double* __restrict__ tot,
                                                     const int32_t* __restrict__ fidx, const float* __restrict__ w,
@@ -346,9 +348,15 @@ __global__ void __launch_bounds__(256) k_sample_bwd(const float* __restrict__ gy
     for (int c = 0; c < 3; ++c) {
         const long long v = faces[3 * (size_t)fi + c] + o;
         const float wc = w[3 * (base + i) + c];
-        atomicAdd(gverts + 3 * v, wc * gx[0]);
-        atomicAdd(gverts + 3 * v + 1, wc * gx[1]);
-        atomicAdd(gverts + 3 * v + 2, wc * gx[2]);
+        if (PAD4) {
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gverts + 4 * v), "f"(wc * gx[0]), "f"(wc * gx[1]),
+                         "f"(wc * gx[2]), "f"(0.f)
+                         : "memory");
+        } else {
+            atomicAdd(gverts + 3 * v, wc * gx[0]);
+            atomicAdd(gverts + 3 * v + 1, wc * gx[1]);
+            atomicAdd(gverts + 3 * v + 2, wc * gx[2]);
+        }
     }
 }
 
@@ -401,15 +409,31 @@ extern "C" int mrb_normalize_cloud_fwd(const float* raw, int B, int n, float* cl
     return check_launch("normalize_cloud_fwd");
 }
 
-extern "C" int mrb_sample_points_bwd(const float* gcloud, const float* cloud, const double* stats, const int32_t* fidx,
-                                     const float* w, const long long* faces, const int32_t* v_off, int B, int n,
-                                     float* gverts, double* scratch, void* stream_) {
+static int launch_sample_bwd(const float* gcloud, const float* cloud, const double* stats, const int32_t* fidx, const float* w,
+                             const long long* faces, const int32_t* v_off, int B, int n, float* gverts, int ld_gverts,
+                             double* scratch, void* stream_) {
     MRB_REQUIRE(gcloud && cloud && stats && fidx && w && faces && v_off && gverts && scratch, "sample_points_bwd: null pointer");
     MRB_REQUIRE(B <= 65535, "sample_points_bwd: batch too large");
+    MRB_REQUIRE(ld_gverts == 3 || (ld_gverts == 4 && ((uintptr_t)gverts & 15) == 0),
+                "sample_points_bwd: gradient rows must be 3 floats, or 4 floats and 16-byte aligned (got ld = %d)", ld_gverts);
     if (B == 0 || n == 0) return MRB_OK;
     cudaStream_t s = (cudaStream_t)stream_;
     cudaMemsetAsync(scratch, 0, sizeof(double) * 4 * (size_t)B, s);
     k_sample_bwd_sums<<<dim3(BWD_SPLIT, B), 256, 0, s>>>(gcloud, cloud, n, scratch);
-    k_sample_bwd<<<dim3(ceil_div(n, 256), B), 256, 0, s>>>(gcloud, cloud, stats, scratch, fidx, w, faces, v_off, n, gverts);
+    const dim3 grid(ceil_div(n, 256), B);
+    if (ld_gverts == 4) k_sample_bwd<true><<<grid, 256, 0, s>>>(gcloud, cloud, stats, scratch, fidx, w, faces, v_off, n, gverts);
+    else k_sample_bwd<false><<<grid, 256, 0, s>>>(gcloud, cloud, stats, scratch, fidx, w, faces, v_off, n, gverts);
     return check_launch("sample_points_bwd");
+}
+
+extern "C" int mrb_sample_points_bwd(const float* gcloud, const float* cloud, const double* stats, const int32_t* fidx,
+                                     const float* w, const long long* faces, const int32_t* v_off, int B, int n,
+                                     float* gverts, double* scratch, void* stream_) {
+    return launch_sample_bwd(gcloud, cloud, stats, fidx, w, faces, v_off, B, n, gverts, 3, scratch, stream_);
+}
+
+extern "C" int mrb_sample_points_bwd_ld(const float* gcloud, const float* cloud, const double* stats, const int32_t* fidx,
+                                        const float* w, const long long* faces, const int32_t* v_off, int B, int n,
+                                        float* gverts, int ld_gverts, double* scratch, void* stream_) {
+    return launch_sample_bwd(gcloud, cloud, stats, fidx, w, faces, v_off, B, n, gverts, ld_gverts, scratch, stream_);
 }

@@ -983,11 +983,12 @@ class _Sample(torch.autograd.Function):
             return (None,) * 13
         cloud, stats, fidx, w, f, v_off = ctx.saved_tensors
         B, n, vshape = ctx.dims
-        gverts = torch.zeros(vshape, dtype=torch.float32, device=cloud.device)
+        # rows padded to 4 floats: one 16-byte vector reduction per face corner; the V x 3 view is the gradient
+        gverts = torch.zeros(vshape[0], 4, dtype=torch.float32, device=cloud.device)
         scratch = torch.empty(4 * B, dtype=torch.float64, device=cloud.device)
-        _lib.call("mrb_sample_points_bwd", _lib.ptr(_f32c(gcloud)), _lib.ptr(cloud), _lib.ptr(stats), _lib.ptr(fidx),
-                  _lib.ptr(w), _lib.ptr(f), _lib.ptr(v_off), B, n, _lib.ptr(gverts), _lib.ptr(scratch))
-        return (gverts,) + (None,) * 12
+        _lib.call("mrb_sample_points_bwd_ld", _lib.ptr(_f32c(gcloud)), _lib.ptr(cloud), _lib.ptr(stats), _lib.ptr(fidx),
+                  _lib.ptr(w), _lib.ptr(f), _lib.ptr(v_off), B, n, _lib.ptr(gverts), 4, _lib.ptr(scratch))
+        return (gverts[:, :3],) + (None,) * 12
 
 
 def _face_cdf(v: Tensor, f: Tensor, v_off: Tensor, f_off: Tensor, B: int, max_faces: int) -> Tensor:
@@ -1222,6 +1223,15 @@ def weighted_scalar_sum(xs: Sequence[Tensor], weights: Optional[Sequence[float]]
     return _ScalarCombine.apply(tuple([1.0] * len(xs) if weights is None else weights), *xs)
 
 
+def _normals_bwd(pts: Tensor, knn: Tensor, k: int, gn: Tensor) -> Tensor:
+    """Gradient of the estimated normals w.r.t. the points.  The kernel scatters into rows padded to 4 floats (one 16-byte
+    vector reduction per neighbour instead of three scalar atomics); the B x P x 3 view of that buffer is returned."""
+    B, P, _ = pts.shape
+    g4 = torch.zeros(B, P, 4, dtype=torch.float32, device=pts.device)
+    _lib.call("mrb_normals_bwd_ld", _lib.ptr(pts), _lib.ptr(knn), B, P, k, _lib.ptr(gn), _lib.ptr(g4), 4)
+    return g4[..., :3]
+
+
 class _NormalLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, p, q, knn_p, knn_q, idx_p, idx_q):
@@ -1262,11 +1272,9 @@ class _NormalLoss(torch.autograd.Function):
                   _lib.ptr(z(g0)), _lib.ptr(z(g1)), _lib.ptr(gnp), _lib.ptr(gnq))
         gp = gq = None
         if need_p:
-            gp = torch.zeros_like(pc)
-            _lib.call("mrb_normals_bwd", _lib.ptr(pc), _lib.ptr(knn_p), B, P, k, _lib.ptr(gnp), _lib.ptr(gp))
+            gp = _normals_bwd(pc, knn_p, k, gnp)
         if need_q:
-            gq = torch.zeros_like(qc)
-            _lib.call("mrb_normals_bwd", _lib.ptr(qc), _lib.ptr(knn_q), B, Q, k, _lib.ptr(gnq), _lib.ptr(gq))
+            gq = _normals_bwd(qc, knn_q, k, gnq)
         return gp, gq, None, None, None, None
 
 
@@ -1311,11 +1319,9 @@ class _NormalLossTotal(torch.autograd.Function):
                   _lib.ptr(_f32c(g).reshape(1)), ctx.scale, _lib.ptr(gnp), _lib.ptr(gnq))
         gp = gq = None
         if need_p:
-            gp = torch.zeros_like(pc)
-            _lib.call("mrb_normals_bwd", _lib.ptr(pc), _lib.ptr(knn_p), B, P, k, _lib.ptr(gnp), _lib.ptr(gp))
+            gp = _normals_bwd(pc, knn_p, k, gnp)
         if need_q:
-            gq = torch.zeros_like(qc)
-            _lib.call("mrb_normals_bwd", _lib.ptr(qc), _lib.ptr(knn_q), B, Q, k, _lib.ptr(gnq), _lib.ptr(gq))
+            gq = _normals_bwd(qc, knn_q, k, gnq)
         return gp, gq, None, None, None, None, None
 
 

@@ -235,6 +235,45 @@ def test_normals_eigenvectors_vs_oracle(lib):
     assert torch.allclose(got.norm(dim=2).cpu(), torch.ones(B, P), atol=1e-5)
 
 
+def test_padded_gradient_rows_equal_packed_rows(lib):
+    """C ABI: mrb_normals_bwd_ld / mrb_sample_points_bwd_ld with 4-float rows (vector reductions) against the 3-float
+    entry points (scalar atomics); only the summation order differs."""
+    from meshrcnn_b200 import _lib
+    gen = torch.Generator().manual_seed(9)
+    B, P, k = 3, 700, 10
+    pt = torch.rand(B, P, 3, generator=gen).cuda()
+    nn = torch.randint(0, P, (B, P, k), generator=gen, dtype=torch.int32).cuda()
+    gn = torch.randn(B, P, 3, generator=gen).cuda()
+    g3 = torch.zeros(B, P, 3, device="cuda")
+    g4 = torch.zeros(B, P, 4, device="cuda")
+    _lib.call("mrb_normals_bwd", _lib.ptr(pt), _lib.ptr(nn), B, P, k, _lib.ptr(gn), _lib.ptr(g3))
+    _lib.call("mrb_normals_bwd_ld", _lib.ptr(pt), _lib.ptr(nn), B, P, k, _lib.ptr(gn), _lib.ptr(g4), 4)
+    assert float(g4[..., 3].abs().max()) == 0.0
+    scale = float(g3.abs().max())
+    assert scale > 0 and float((g4[..., :3] - g3).abs().max()) <= 2e-5 * scale
+    with pytest.raises(RuntimeError):
+        _lib.call("mrb_normals_bwd_ld", _lib.ptr(pt), _lib.ptr(nn), B, P, k, _lib.ptr(gn), _lib.ptr(g4), 5)
+    # sampling backward: two tetrahedra, 300 points each
+    verts = torch.rand(8, 3, generator=gen).cuda()
+    faces = torch.tensor([[0, 1, 2], [0, 1, 3], [0, 2, 3], [1, 2, 3]] * 2).cuda()
+    v_off = torch.tensor([0, 4, 8], dtype=torch.int32).cuda()
+    n = 300
+    cloud = torch.rand(2, n, 3, generator=gen).cuda()
+    gcloud = torch.randn(2, n, 3, generator=gen).cuda()
+    stats = torch.zeros(2, 8, dtype=torch.float64).cuda()
+    stats[:, 3] = 1.5
+    stats[:, 4] = torch.tensor([7.0, -1.0], dtype=torch.float64).cuda()
+    fidx = torch.cat([torch.randint(0, 4, (1, n), generator=gen), torch.randint(4, 8, (1, n), generator=gen)]).int().cuda()
+    w = torch.rand(2, n, 3, generator=gen).cuda()
+    out3, out4 = torch.zeros(8, 3, device="cuda"), torch.zeros(8, 4, device="cuda")
+    scr = torch.empty(8, dtype=torch.float64, device="cuda")
+    args = (_lib.ptr(gcloud), _lib.ptr(cloud), _lib.ptr(stats), _lib.ptr(fidx), _lib.ptr(w), _lib.ptr(faces), _lib.ptr(v_off), 2, n)
+    _lib.call("mrb_sample_points_bwd", *args, _lib.ptr(out3), _lib.ptr(scr))
+    _lib.call("mrb_sample_points_bwd_ld", *args, _lib.ptr(out4), 4, _lib.ptr(scr))
+    assert float(out4[:, 3].abs().max()) == 0.0
+    assert float((out4[:, :3] - out3).abs().max()) <= 2e-5 * float(out3.abs().max())
+
+
 def test_batched_mesh_loss_runs_and_is_finite(lib):
     """Three stages, own RNG, gradient reaches the positions (shape/finite check at 10k points)."""
     from meshrcnn_b200 import loss_functions as LF, synthetic
