@@ -161,6 +161,15 @@ __global__ void __launch_bounds__(256) k_skinny_k(int M, int N, int K, const flo
 // takes rows w, w + 8, ... of the chunk, lanes stride over the N <= 256 columns (coalesced), the 8 warps' partial sums are
 // combined in shared memory one output row at a time (every index into acc[][] is a compile-time constant, so the
 // partial sums stay in registers) and added to C with one atomic per element and block.
+// rows in flight per warp / blocks per SM, measured at C[3 x 128] = gpre^T x with 50 k (206 k) rows (scripts/simt_variants.sh):
+// 2 / 4: 27.3 (66.7) us; 4 / 4: 20.3 (42.0); 4 / 2: 17.9 (41.7); 6 / 2: 17.9 (38.2); 4 / 8: 19.8 (44.4)
+#ifndef MRB_SK_TN_ROWS
+#define MRB_SK_TN_ROWS 4
+#endif
+#ifndef MRB_SK_TN_RPB_DIV
+#define MRB_SK_TN_RPB_DIV 2
+#endif
+constexpr int SK_TN_ROWS = MRB_SK_TN_ROWS;
 template <int MACC>
 __global__ void __launch_bounds__(256) k_skinny_tn(int M, int N, int K, const float* __restrict__ A, int lda,
                                                    const float* __restrict__ B, int ldb, float* __restrict__ C, int scm,
@@ -173,27 +182,29 @@ __global__ void __launch_bounds__(256) k_skinny_tn(int M, int N, int K, const fl
     for (int m = 0; m < MACC; ++m)
 #pragma unroll
         for (int j = 0; j < JMAX; ++j) acc[m][j] = 0.f;
-    // two rows of the chunk per iteration: their loads are all issued before the first FMA (the loop is latency bound: a
-    // warp owns only ~10 rows)
-    for (int k = k0 + warp_id(); k < k1; k += 16) {
-        const int kb = min(k + 8, k1 - 1);
-        const bool has_b = k + 8 < k1;
-        float a[MACC], a2[MACC], b[JMAX], b2[JMAX];
+    // SK_TN_ROWS rows of the chunk per iteration: their loads are all issued before the first FMA (the loop is latency bound:
+    // a warp owns only ~10 rows)
+    constexpr int R = SK_TN_ROWS;
+    for (int k = k0 + warp_id(); k < k1; k += 8 * R) {
+        float a[R][MACC], b[R][JMAX];
 #pragma unroll
-        for (int m = 0; m < MACC; ++m) {
-            a[m] = (m < M) ? __ldg(A + (size_t)k * lda + m) : 0.f;
-            a2[m] = (m < M && has_b) ? __ldg(A + (size_t)kb * lda + m) : 0.f;
+        for (int r = 0; r < R; ++r) {
+            const int kr = min(k + 8 * r, k1 - 1);
+            const bool has = k + 8 * r < k1;
+#pragma unroll
+            for (int m = 0; m < MACC; ++m) a[r][m] = (m < M && has) ? __ldg(A + (size_t)kr * lda + m) : 0.f;
+#pragma unroll
+            for (int j = 0; j < JMAX; ++j) {
+                const int n = j * 32 + lane_id();
+                b[r][j] = (n < N) ? __ldg(B + (size_t)kr * ldb + n) : 0.f;
+            }
         }
 #pragma unroll
-        for (int j = 0; j < JMAX; ++j) {
-            const int n = j * 32 + lane_id();
-            b[j] = (n < N) ? __ldg(B + (size_t)k * ldb + n) : 0.f;
-            b2[j] = (n < N) ? __ldg(B + (size_t)kb * ldb + n) : 0.f;
-        }
+        for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int j = 0; j < JMAX; ++j)
+            for (int j = 0; j < JMAX; ++j)
 #pragma unroll
-            for (int m = 0; m < MACC; ++m) acc[m][j] = fmaf(a2[m], b2[j], fmaf(a[m], b[j], acc[m][j]));
+                for (int m = 0; m < MACC; ++m) acc[m][j] = fmaf(a[r][m], b[r][j], acc[m][j]);
     }
 #pragma unroll
     for (int m = 0; m < MACC; ++m) {
@@ -207,6 +218,47 @@ __global__ void __launch_bounds__(256) k_skinny_tn(int M, int N, int K, const fl
 #pragma unroll
             for (int w = 0; w < 8; ++w) v += red[w][n];
             atomicAdd(C + (size_t)m * scm + (size_t)n * scn, v);
+        }
+    }
+}
+
+// C[M x N] += A[K x M]^T * B[K x N] with M, N <= 4 (e.g. the position block of the head's weight gradient, 3 x 3 over all
+// vertices): one thread per row of the long K dimension, 16 register accumulators, warp shuffles + one atomic per element
+// and block.  (k_skinny_tn would use 3 of 32 lanes.)
+__global__ void __launch_bounds__(256) k_tiny_tn(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                 const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc) {
+    float acc[4][4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) acc[m][n] = 0.f;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
+        float a[4], b[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) a[m] = (m < M) ? __ldg(A + (size_t)k * lda + m) : 0.f;
+#pragma unroll
+        for (int n = 0; n < 4; ++n) b[n] = (n < N) ? __ldg(B + (size_t)k * ldb + n) : 0.f;
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int n = 0; n < 4; ++n) acc[m][n] = fmaf(a[m], b[n], acc[m][n]);
+    }
+    __shared__ float red[8][16];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+            const float v = warp_sum(acc[m][n]);
+            if (lane_id() == 0) red[warp_id()][m * 4 + n] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        const int m = threadIdx.x >> 2, n = threadIdx.x & 3;
+        if (m < M && n < N) {
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+            atomicAdd(C + (size_t)m * ldc + n, v);
         }
     }
 }
@@ -234,16 +286,21 @@ extern "C" int mrb_sgemm(int transA, int transB, int M, int N, int K, const floa
         k_skinny_k<<<ceil_div(M, 8), 256, 0, s>>>(M, N, K, A, lda, B, sbk, sbn, beta, C, ldc);
         return check_launch("sgemm");
     }
+    if (K > 0 && transA && !transB && M <= 4 && N <= 4) {           // reduction over the long K into a tiny C
+        k_scale_rows<<<1, 256, 0, s>>>(C, M, N, ldc, beta);
+        k_tiny_tn<<<min(ceil_div(K, 256), 2 * kNumSMs), 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc);
+        return check_launch("sgemm");
+    }
     if (K > 0 && transA && !transB && M <= SKINNY && N <= 256) {    // reduction over the long K into a skinny-row C
         k_scale_rows<<<(unsigned)ceil_div64((long long)M * N, 256), 256, 0, s>>>(C, M, N, ldc, beta);
-        const int rpb = max(64, ceil_div(K, 4 * kNumSMs));     // (2 blocks per SM with 4x the rows each measured 2.4x slower)
+        const int rpb = max(64, ceil_div(K, MRB_SK_TN_RPB_DIV * kNumSMs));
         if (M <= 4) k_skinny_tn<4><<<ceil_div(K, rpb), 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, 1, rpb);
         else k_skinny_tn<SKINNY><<<ceil_div(K, rpb), 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, 1, rpb);
         return check_launch("sgemm");
     }
     if (K > 0 && transA && !transB && N <= SKINNY && M <= 256) {    // same with a skinny-column C: C^T = B^T A
         k_scale_rows<<<(unsigned)ceil_div64((long long)M * N, 256), 256, 0, s>>>(C, M, N, ldc, beta);
-        const int rpb = max(64, ceil_div(K, 4 * kNumSMs));     // (2 blocks per SM with 4x the rows each measured 2.4x slower)
+        const int rpb = max(64, ceil_div(K, MRB_SK_TN_RPB_DIV * kNumSMs));
         if (N <= 4) k_skinny_tn<4><<<ceil_div(K, rpb), 256, 0, s>>>(N, M, K, B, ldb, A, lda, C, 1, ldc, rpb);
         else k_skinny_tn<SKINNY><<<ceil_div(K, rpb), 256, 0, s>>>(N, M, K, B, ldb, A, lda, C, 1, ldc, rpb);
         return check_launch("sgemm");

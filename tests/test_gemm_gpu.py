@@ -112,7 +112,8 @@ def test_tc_gemm_accumulate_and_wgrad_split(lib):
 
 @pytest.mark.parametrize("ta,tb,M,N,K", [(0, 1, 5000, 3, 131), (0, 0, 5000, 131, 3), (1, 0, 3, 131, 5000), (0, 1, 77, 8, 40),
                                          (1, 0, 8, 300, 999), (0, 0, 100, 50, 70), (1, 1, 33, 65, 129), (1, 0, 131, 128, 4000),
-                                         (0, 0, 5000, 3, 128), (0, 1, 5000, 128, 3), (1, 0, 128, 3, 5000), (1, 0, 200, 6, 3000)])
+                                         (0, 0, 5000, 3, 128), (0, 1, 5000, 128, 3), (1, 0, 128, 3, 5000), (1, 0, 200, 6, 3000),
+                                         (1, 0, 3, 3, 50353), (1, 0, 4, 1, 777), (1, 0, 3, 128, 50353)])
 def test_sgemm_simt_all_paths(lib, ta, tb, M, N, K):
     """Exact-fp32 CUDA-core GEMM incl. the skinny special cases of the 3-wide heads, with beta accumulation."""
     from meshrcnn_b200 import _lib
