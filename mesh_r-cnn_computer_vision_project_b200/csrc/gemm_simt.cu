@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) k_skinny_k(int M, int N, int K, const flo
 // takes rows w, w + 8, ... of the chunk, lanes stride over the N <= 256 columns (coalesced), the 8 warps' partial sums are
 // combined in shared memory one output row at a time (every index into acc[][] is a compile-time constant, so the
 // partial sums stay in registers) and added to C with one atomic per element and block.
-// rows in flight per warp / blocks per SM, measured at C[3 x 128] = gpre^T x with 50 k (206 k) rows (scripts/simt_variants.sh):
+// rows in flight per warp / blocks per SM, measured at C[3 x 128] = gpre^T x with 50 k (206 k) rows (scripts/variants.sh gemm_simt.cu "python scripts/time_skinny.py"):
 // 2 / 4: 27.3 (66.7) us; 4 / 4: 20.3 (42.0); 4 / 2: 17.9 (41.7); 6 / 2: 17.9 (38.2); 4 / 8: 19.8 (44.4)
 #ifndef MRB_SK_TN_ROWS
 #define MRB_SK_TN_ROWS 4

@@ -103,6 +103,12 @@ __device__ __forceinline__ void neighbourhood(const float* __restrict__ pt, cons
     }
 }
 
+// resident blocks per SM asked of ptxas for the backward kernel (scripts/variants.sh normals.cu "python scripts/time_normals.py"):
+// 1 (145 registers): 67.4 us; 5 (96): 59.4; 6 (80, 48 B spills): 59.4; 8 (64): 65.5; 10 (48): 80.5.  The forward kernel is flat
+// (43 - 44 us for 1 .. 8).
+#ifndef MRB_NORMALS_MINB
+#define MRB_NORMALS_MINB 5
+#endif
 template <int KT>
 __global__ void __launch_bounds__(128) k_normals_fwd(const float* __restrict__ pt, const int32_t* __restrict__ knn, int P,
                                                      int k, float* __restrict__ normals) {
@@ -123,7 +129,7 @@ __global__ void __launch_bounds__(128) k_normals_fwd(const float* __restrict__ p
 // PAD4: gpt rows are 4 floats wide (xyz + one unused lane), so a neighbour's three partial sums go out as ONE 16-byte
 // red.global.add.v4.f32 instead of three scalar atomics (the kernel is bound by the L2 atomic units: 30 -> 10 per point).
 template <int KT, bool PAD4>
-__global__ void __launch_bounds__(128) k_normals_bwd(const float* __restrict__ pt, const int32_t* __restrict__ knn, int P,
+__global__ void __launch_bounds__(128, MRB_NORMALS_MINB) k_normals_bwd(const float* __restrict__ pt, const int32_t* __restrict__ knn, int P,
                                                      int k, const float* __restrict__ gn, float* __restrict__ gpt) {
     const int batch = blockIdx.y;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
