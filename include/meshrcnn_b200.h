@@ -268,15 +268,19 @@ int mrb_chamfer_bwd(const float* a, const float* b, int B, int P, int Q, const i
  *   mrb_normals_fwd     normal[b,p] = row 0 of the (ascending, canonically signed) eigenvector matrix of the 3x3
  *                       scatter matrix of pt[b, knn[b,p,:]]
  *   mrb_normals_bwd     gn -> gpt (atomic accumulate into B x P x 3)
+ *   mrb_normals_fwd_eig also writes the eigen-decomposition: eig = 12 planes of B * P doubles (w0 w1 w2 | V row-major)
  *   mrb_normals_bwd_ld  the same into rows of ld_gpt floats: 3, or 4 (xyz + one unused lane, 16-byte aligned) -- the padded
- *                       layout turns the 3 scalar atomics per neighbour into one 16-byte vector reduction
+ *                       layout turns the 3 scalar atomics per neighbour into one 16-byte vector reduction; eig (may be
+ *                       NULL) = the planes mrb_normals_fwd_eig wrote for the same pt / knn: the Jacobi sweeps are skipped
  *   mrb_normal_loss_fwd out2[0] = sum_i |na_i . nb_idx_a[i]|, out2[1] = sum_j |nb_j . na_idx_b[j]|
  *   mrb_edge_loss_fwd   out[0] = mean over the E directed edges of |v_r - v_c|^2
  */
 int mrb_normals_fwd(const float* pt, const int32_t* knn, int B, int P, int k, float* normals_out, void* stream);
 int mrb_normals_bwd(const float* pt, const int32_t* knn, int B, int P, int k, const float* gn, float* gpt, void* stream);
+int mrb_normals_fwd_eig(const float* pt, const int32_t* knn, int B, int P, int k, float* normals_out, double* eig,
+                        void* stream);
 int mrb_normals_bwd_ld(const float* pt, const int32_t* knn, int B, int P, int k, const float* gn, float* gpt, int ld_gpt,
-                       void* stream);
+                       const double* eig, void* stream);
 int mrb_normal_loss_fwd(const float* na, const float* nb, int B, int P, int Q, const int32_t* idx_a, const int32_t* idx_b,
                         double* acc2, float* out2, void* stream);
 int mrb_normal_loss_bwd(const float* na, const float* nb, int B, int P, int Q, const int32_t* idx_a, const int32_t* idx_b,

@@ -111,7 +111,8 @@ __device__ __forceinline__ void neighbourhood(const float* __restrict__ pt, cons
 #endif
 template <int KT>
 __global__ void __launch_bounds__(128) k_normals_fwd(const float* __restrict__ pt, const int32_t* __restrict__ knn, int P,
-                                                     int k, float* __restrict__ normals) {
+                                                     int k, float* __restrict__ normals, double* __restrict__ eig,
+                                                     size_t eig_plane) {
     const int batch = blockIdx.y;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
@@ -122,6 +123,12 @@ __global__ void __launch_bounds__(128) k_normals_fwd(const float* __restrict__ p
     normals[3 * o] = (float)V[0][0];
     normals[3 * o + 1] = (float)V[0][1];
     normals[3 * o + 2] = (float)V[0][2];
+    if (eig) {      // 12 planes of B * P doubles (w0 w1 w2 | V row-major): the backward pass skips the Jacobi sweeps
+#pragma unroll
+        for (int c = 0; c < 3; ++c) eig[c * eig_plane + o] = w[c];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) eig[(3 + c) * eig_plane + o] = V[c / 3][c % 3];
+    }
 }
 
 // gn -> gpt (atomic scatter to the gathered rows):  n_j = V[0][j]
@@ -130,7 +137,8 @@ __global__ void __launch_bounds__(128) k_normals_fwd(const float* __restrict__ p
 // red.global.add.v4.f32 instead of three scalar atomics (the kernel is bound by the L2 atomic units: 30 -> 10 per point).
 template <int KT, bool PAD4>
 __global__ void __launch_bounds__(128, MRB_NORMALS_MINB) k_normals_bwd(const float* __restrict__ pt, const int32_t* __restrict__ knn, int P,
-                                                     int k, const float* __restrict__ gn, float* __restrict__ gpt) {
+                                                     int k, const float* __restrict__ gn, float* __restrict__ gpt,
+                                                     const double* __restrict__ eig, size_t eig_plane) {
     const int batch = blockIdx.y;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
@@ -140,7 +148,14 @@ __global__ void __launch_bounds__(128, MRB_NORMALS_MINB) k_normals_bwd(const flo
     double Y[KMAX][3], S[6], w[3], V[3][3];
     const int32_t* nn = knn + o * k;
     neighbourhood<KT>(pt + (size_t)batch * P * 3, nn, k, Y, S);
-    eigh3(S, w, V);
+    if (eig) {      // eigen-decomposition saved by the forward pass
+#pragma unroll
+        for (int c = 0; c < 3; ++c) w[c] = eig[c * eig_plane + o];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) V[c / 3][c % 3] = eig[(3 + c) * eig_plane + o];
+    } else {
+        eigh3(S, w, V);
+    }
     double Kf[3][3];
     const double tiny = 1e-14 * (fabs(w[0]) + fabs(w[1]) + fabs(w[2])) + 1e-300;
     for (int i = 0; i < 3; ++i)
@@ -281,18 +296,29 @@ __global__ void __launch_bounds__(256) k_edge_bwd(const float* __restrict__ pos,
 using namespace mrb;
 using namespace mrb::normals;
 
-extern "C" int mrb_normals_fwd(const float* pt, const int32_t* knn, int B, int P, int k, float* normals_out, void* stream_) {
+static int launch_normals_fwd(const float* pt, const int32_t* knn, int B, int P, int k, float* normals_out, double* eig,
+                              void* stream_) {
     MRB_REQUIRE(pt && knn && normals_out, "normals_fwd: null pointer");
     MRB_REQUIRE(k >= 1 && k <= KMAX, "normals_fwd: k must be in [1, %d]", KMAX);
     if (B == 0 || P == 0) return MRB_OK;
     const dim3 grid(ceil_div(P, 128), B);
-    if (k == 10) k_normals_fwd<10><<<grid, 128, 0, (cudaStream_t)stream_>>>(pt, knn, P, k, normals_out);       // the reference default
-    else k_normals_fwd<0><<<grid, 128, 0, (cudaStream_t)stream_>>>(pt, knn, P, k, normals_out);
+    const size_t plane = (size_t)B * P;
+    if (k == 10) k_normals_fwd<10><<<grid, 128, 0, (cudaStream_t)stream_>>>(pt, knn, P, k, normals_out, eig, plane);   // the reference default
+    else k_normals_fwd<0><<<grid, 128, 0, (cudaStream_t)stream_>>>(pt, knn, P, k, normals_out, eig, plane);
     return check_launch("normals_fwd");
 }
 
+extern "C" int mrb_normals_fwd(const float* pt, const int32_t* knn, int B, int P, int k, float* normals_out, void* stream_) {
+    return launch_normals_fwd(pt, knn, B, P, k, normals_out, nullptr, stream_);
+}
+
+extern "C" int mrb_normals_fwd_eig(const float* pt, const int32_t* knn, int B, int P, int k, float* normals_out, double* eig,
+                                   void* stream_) {
+    return launch_normals_fwd(pt, knn, B, P, k, normals_out, eig, stream_);
+}
+
 static int launch_normals_bwd(const float* pt, const int32_t* knn, int B, int P, int k, const float* gn, float* gpt, int ld_gpt,
-                              void* stream_) {
+                              const double* eig, void* stream_) {
     MRB_REQUIRE(pt && knn && gn && gpt, "normals_bwd: null pointer");
     MRB_REQUIRE(k >= 1 && k <= KMAX, "normals_bwd: k must be in [1, %d]", KMAX);
     MRB_REQUIRE(ld_gpt == 3 || (ld_gpt == 4 && ((uintptr_t)gpt & 15) == 0),
@@ -300,24 +326,25 @@ static int launch_normals_bwd(const float* pt, const int32_t* knn, int B, int P,
     if (B == 0 || P == 0) return MRB_OK;
     const dim3 grid(ceil_div(P, 128), B);
     cudaStream_t s = (cudaStream_t)stream_;
+    const size_t plane = (size_t)B * P;
     if (ld_gpt == 4) {
-        if (k == 10) k_normals_bwd<10, true><<<grid, 128, 0, s>>>(pt, knn, P, k, gn, gpt);
-        else k_normals_bwd<0, true><<<grid, 128, 0, s>>>(pt, knn, P, k, gn, gpt);
+        if (k == 10) k_normals_bwd<10, true><<<grid, 128, 0, s>>>(pt, knn, P, k, gn, gpt, eig, plane);
+        else k_normals_bwd<0, true><<<grid, 128, 0, s>>>(pt, knn, P, k, gn, gpt, eig, plane);
     } else {
-        if (k == 10) k_normals_bwd<10, false><<<grid, 128, 0, s>>>(pt, knn, P, k, gn, gpt);
-        else k_normals_bwd<0, false><<<grid, 128, 0, s>>>(pt, knn, P, k, gn, gpt);
+        if (k == 10) k_normals_bwd<10, false><<<grid, 128, 0, s>>>(pt, knn, P, k, gn, gpt, eig, plane);
+        else k_normals_bwd<0, false><<<grid, 128, 0, s>>>(pt, knn, P, k, gn, gpt, eig, plane);
     }
     return check_launch("normals_bwd");
 }
 
 extern "C" int mrb_normals_bwd(const float* pt, const int32_t* knn, int B, int P, int k, const float* gn, float* gpt,
                                void* stream_) {
-    return launch_normals_bwd(pt, knn, B, P, k, gn, gpt, 3, stream_);
+    return launch_normals_bwd(pt, knn, B, P, k, gn, gpt, 3, nullptr, stream_);
 }
 
 extern "C" int mrb_normals_bwd_ld(const float* pt, const int32_t* knn, int B, int P, int k, const float* gn, float* gpt,
-                                  int ld_gpt, void* stream_) {
-    return launch_normals_bwd(pt, knn, B, P, k, gn, gpt, ld_gpt, stream_);
+                                  int ld_gpt, const double* eig, void* stream_) {
+    return launch_normals_bwd(pt, knn, B, P, k, gn, gpt, ld_gpt, eig, stream_);
 }
 
 extern "C" int mrb_normal_loss_fwd(const float* na, const float* nb, int B, int P, int Q, const int32_t* idx_a,

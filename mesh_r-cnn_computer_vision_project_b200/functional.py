@@ -1223,12 +1223,22 @@ def weighted_scalar_sum(xs: Sequence[Tensor], weights: Optional[Sequence[float]]
     return _ScalarCombine.apply(tuple([1.0] * len(xs) if weights is None else weights), *xs)
 
 
-def _normals_bwd(pts: Tensor, knn: Tensor, k: int, gn: Tensor) -> Tensor:
+def _normals_fwd(pts: Tensor, knn: Tensor, k: int, keep_eig: bool):
+    """(normals B x P x 3, eig | None).  ``keep_eig``: also keep the fp64 eigen-decomposition (12 planes of B * P doubles) for
+    the backward pass, which then skips the Jacobi sweeps."""
+    B, P, _ = pts.shape
+    n = torch.empty(B, P, 3, dtype=torch.float32, device=pts.device)
+    eig = torch.empty(12, B * P, dtype=torch.float64, device=pts.device) if keep_eig else None
+    _lib.call("mrb_normals_fwd_eig", _lib.ptr(pts), _lib.ptr(knn), B, P, k, _lib.ptr(n), _lib.ptr(eig))
+    return n, eig
+
+
+def _normals_bwd(pts: Tensor, knn: Tensor, k: int, gn: Tensor, eig: Optional[Tensor]) -> Tensor:
     """Gradient of the estimated normals w.r.t. the points.  The kernel scatters into rows padded to 4 floats (one 16-byte
     vector reduction per neighbour instead of three scalar atomics); the B x P x 3 view of that buffer is returned."""
     B, P, _ = pts.shape
     g4 = torch.zeros(B, P, 4, dtype=torch.float32, device=pts.device)
-    _lib.call("mrb_normals_bwd_ld", _lib.ptr(pts), _lib.ptr(knn), B, P, k, _lib.ptr(gn), _lib.ptr(g4), 4)
+    _lib.call("mrb_normals_bwd_ld", _lib.ptr(pts), _lib.ptr(knn), B, P, k, _lib.ptr(gn), _lib.ptr(g4), 4, _lib.ptr(eig))
     return g4[..., :3]
 
 
@@ -1246,10 +1256,9 @@ class _NormalLoss(torch.autograd.Function):
         dev = p.device
         i32 = lambda t: t.to(torch.int32).contiguous()
         knn_p, knn_q, idx_p, idx_q = i32(knn_p), i32(knn_q), i32(idx_p), i32(idx_q)
-        n_p = torch.empty(B, P, 3, dtype=torch.float32, device=dev)
-        n_q = torch.empty(B, Q, 3, dtype=torch.float32, device=dev)
-        _lib.call("mrb_normals_fwd", _lib.ptr(pc), _lib.ptr(knn_p), B, P, k, _lib.ptr(n_p))
-        _lib.call("mrb_normals_fwd", _lib.ptr(qc), _lib.ptr(knn_q), B, Q, k, _lib.ptr(n_q))
+        n_p, eig_p = _normals_fwd(pc, knn_p, k, ctx.needs_input_grad[0])
+        n_q, eig_q = _normals_fwd(qc, knn_q, k, ctx.needs_input_grad[1])
+        ctx.eig = (eig_p, eig_q)         # plain attributes: not inputs / outputs of the node
         acc = torch.empty(2, dtype=torch.float64, device=dev)
         out = torch.empty(2, dtype=torch.float32, device=dev)
         _lib.call("mrb_normal_loss_fwd", _lib.ptr(n_p), _lib.ptr(n_q), B, P, Q, _lib.ptr(idx_p), _lib.ptr(idx_q),
@@ -1272,9 +1281,9 @@ class _NormalLoss(torch.autograd.Function):
                   _lib.ptr(z(g0)), _lib.ptr(z(g1)), _lib.ptr(gnp), _lib.ptr(gnq))
         gp = gq = None
         if need_p:
-            gp = _normals_bwd(pc, knn_p, k, gnp)
+            gp = _normals_bwd(pc, knn_p, k, gnp, ctx.eig[0])
         if need_q:
-            gq = _normals_bwd(qc, knn_q, k, gnq)
+            gq = _normals_bwd(qc, knn_q, k, gnq, ctx.eig[1])
         return gp, gq, None, None, None, None
 
 
@@ -1294,10 +1303,9 @@ class _NormalLossTotal(torch.autograd.Function):
         dev = p.device
         i32 = lambda t: t if (t.dtype == torch.int32 and t.is_contiguous()) else t.to(torch.int32).contiguous()
         knn_p, knn_q, idx_p, idx_q = i32(knn_p), i32(knn_q), i32(idx_p), i32(idx_q)
-        n_p = torch.empty(B, P, 3, dtype=torch.float32, device=dev)
-        n_q = torch.empty(B, Q, 3, dtype=torch.float32, device=dev)
-        _lib.call("mrb_normals_fwd", _lib.ptr(pc), _lib.ptr(knn_p), B, P, k, _lib.ptr(n_p))
-        _lib.call("mrb_normals_fwd", _lib.ptr(qc), _lib.ptr(knn_q), B, Q, k, _lib.ptr(n_q))
+        n_p, eig_p = _normals_fwd(pc, knn_p, k, ctx.needs_input_grad[0])
+        n_q, eig_q = _normals_fwd(qc, knn_q, k, ctx.needs_input_grad[1])
+        ctx.eig = (eig_p, eig_q)         # plain attributes: not inputs / outputs of the node
         acc = torch.empty(2, dtype=torch.float64, device=dev)
         out = torch.empty(1, dtype=torch.float32, device=dev)
         _lib.call("mrb_normal_loss_total_fwd", _lib.ptr(n_p), _lib.ptr(n_q), B, P, Q, _lib.ptr(idx_p), _lib.ptr(idx_q), float(scale),
@@ -1319,9 +1327,9 @@ class _NormalLossTotal(torch.autograd.Function):
                   _lib.ptr(_f32c(g).reshape(1)), ctx.scale, _lib.ptr(gnp), _lib.ptr(gnq))
         gp = gq = None
         if need_p:
-            gp = _normals_bwd(pc, knn_p, k, gnp)
+            gp = _normals_bwd(pc, knn_p, k, gnp, ctx.eig[0])
         if need_q:
-            gq = _normals_bwd(qc, knn_q, k, gnq)
+            gq = _normals_bwd(qc, knn_q, k, gnq, ctx.eig[1])
         return gp, gq, None, None, None, None, None
 
 

@@ -21,5 +21,9 @@ def timeit(run, reps=10):
         e0.record(); run(); e1.record(); torch.cuda.synchronize(); tot += e0.elapsed_time(e1)
     return tot / reps
 fwd = timeit(lambda: _lib.call("mrb_normals_fwd", _lib.ptr(p), _lib.ptr(kp), B, P, k, _lib.ptr(n)))
-bwd = timeit(lambda: _lib.call("mrb_normals_bwd_ld", _lib.ptr(p), _lib.ptr(kp), B, P, k, _lib.ptr(gn), _lib.ptr(g4), 4))
-print("normals fwd %.1f us  bwd %.1f us  (B=%d P=%d k=%d; |n| mean %.4f)" % (fwd * 1e3, bwd * 1e3, B, P, k, float(n.norm(dim=2).mean())))
+bwd = timeit(lambda: _lib.call("mrb_normals_bwd_ld", _lib.ptr(p), _lib.ptr(kp), B, P, k, _lib.ptr(gn), _lib.ptr(g4), 4, None))
+eig = torch.empty(12, B * P, dtype=torch.float64, device=dev)
+fwd_e = timeit(lambda: _lib.call("mrb_normals_fwd_eig", _lib.ptr(p), _lib.ptr(kp), B, P, k, _lib.ptr(n), _lib.ptr(eig)))
+bwd_e = timeit(lambda: _lib.call("mrb_normals_bwd_ld", _lib.ptr(p), _lib.ptr(kp), B, P, k, _lib.ptr(gn), _lib.ptr(g4), 4, _lib.ptr(eig)))
+print("normals fwd %.1f us  bwd %.1f us | with the saved eigen-decomposition: fwd %.1f us  bwd %.1f us  (B=%d P=%d k=%d; |n| mean %.4f)"
+      % (fwd * 1e3, bwd * 1e3, fwd_e * 1e3, bwd_e * 1e3, B, P, k, float(n.norm(dim=2).mean())))

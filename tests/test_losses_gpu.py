@@ -247,12 +247,21 @@ def test_padded_gradient_rows_equal_packed_rows(lib):
     g3 = torch.zeros(B, P, 3, device="cuda")
     g4 = torch.zeros(B, P, 4, device="cuda")
     _lib.call("mrb_normals_bwd", _lib.ptr(pt), _lib.ptr(nn), B, P, k, _lib.ptr(gn), _lib.ptr(g3))
-    _lib.call("mrb_normals_bwd_ld", _lib.ptr(pt), _lib.ptr(nn), B, P, k, _lib.ptr(gn), _lib.ptr(g4), 4)
+    _lib.call("mrb_normals_bwd_ld", _lib.ptr(pt), _lib.ptr(nn), B, P, k, _lib.ptr(gn), _lib.ptr(g4), 4, None)
     assert float(g4[..., 3].abs().max()) == 0.0
     scale = float(g3.abs().max())
     assert scale > 0 and float((g4[..., :3] - g3).abs().max()) <= 2e-5 * scale
     with pytest.raises(RuntimeError):
-        _lib.call("mrb_normals_bwd_ld", _lib.ptr(pt), _lib.ptr(nn), B, P, k, _lib.ptr(gn), _lib.ptr(g4), 5)
+        _lib.call("mrb_normals_bwd_ld", _lib.ptr(pt), _lib.ptr(nn), B, P, k, _lib.ptr(gn), _lib.ptr(g4), 5, None)
+    # the eigen-decomposition saved by the forward pass gives the same gradient as recomputing it
+    n0, n1 = torch.empty(B, P, 3, device="cuda"), torch.empty(B, P, 3, device="cuda")
+    eig = torch.empty(12, B * P, dtype=torch.float64, device="cuda")
+    _lib.call("mrb_normals_fwd", _lib.ptr(pt), _lib.ptr(nn), B, P, k, _lib.ptr(n0))
+    _lib.call("mrb_normals_fwd_eig", _lib.ptr(pt), _lib.ptr(nn), B, P, k, _lib.ptr(n1), _lib.ptr(eig))
+    assert torch.equal(n0, n1) and torch.equal(eig[3:6].t().float().reshape(B, P, 3), n1)     # normal = row 0 of V
+    g4e = torch.zeros(B, P, 4, device="cuda")
+    _lib.call("mrb_normals_bwd_ld", _lib.ptr(pt), _lib.ptr(nn), B, P, k, _lib.ptr(gn), _lib.ptr(g4e), 4, _lib.ptr(eig))
+    assert float((g4e - g4).abs().max()) <= 2e-5 * scale
     # sampling backward: two tetrahedra, 300 points each
     verts = torch.rand(8, 3, generator=gen).cuda()
     faces = torch.tensor([[0, 1, 2], [0, 1, 3], [0, 2, 3], [1, 2, 3]] * 2).cuda()
