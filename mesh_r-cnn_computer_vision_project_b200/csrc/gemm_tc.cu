@@ -128,8 +128,9 @@ constexpr int PROD_ROWS = BM / PROD_WARPS;
 #define MRB_TC_PREFETCH 2
 #endif
 constexpr int PREFETCH = MRB_TC_PREFETCH;   // A chunks in flight per producer thread (registers)
-// Diagnostic builds (scripts/gemm_variants.sh): -DMRB_DIAG_NOLOAD (producers skip the global loads), -DMRB_DIAG_NOMMA (the
-// issuer skips the MMAs), -DMRB_DIAG_NOSTORE (the epilogue skips the C stores) isolate the three legs of the pipeline.
+// Diagnostic builds (scripts/variants.sh gemm_tc.cu ...): -DMRB_DIAG_NOLOAD (producers skip the global loads), -DMRB_DIAG_NOMMA
+// (the issuer skips the MMAs), -DMRB_DIAG_NOSTORE (the epilogue skips the C stores), -DMRB_DIAG_NOEPI (the epilogue stops after
+// its TMEM reads), -DMRB_DIAG_HALFB (half the weight bytes per chunk) isolate the legs of the pipeline (timing only).
 constexpr int EPI_WARPS = 8;         // epilogue warps: TMEM lane quadrant = warp % 4, column half = (warp - PROD_WARPS) / 4
 constexpr int TC_THREADS = (PROD_WARPS + EPI_WARPS + 2) * 32;   // producers | epilogue warps | MMA issuer | weight TMA
 constexpr int EPI_BYTES = EPI_WARPS * 32 * 33 * 4;
@@ -366,6 +367,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
                     if (warp == PROD_WARPS && lane == 0) TL(1, 41);
                 }
                 const int colbase = n0 + c0;
+#ifdef MRB_DIAG_NOEPI      // timing experiment only: the epilogue ends after the TMEM reads (no transpose, no stores)
+                if (acc[0] != 1.2345e-33f) continue;
+#endif
                 if (aligned && c0 + 32 <= NT && colbase + 32 <= p.N) {
                     // Each thread holds 32 columns of ONE row; storing them directly would touch 32 different 128-byte lines
                     // per instruction.  The block goes through a swizzled (conflict-free) shared-memory tile instead, so
@@ -478,9 +482,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
                     if (use > 0) mbar_wait(empty_bar(s), (use - 1) & 1);
                     TL(3, 60);
                     const uint32_t dst = smem_base + s * STAGE_BYTES + 2 * A_BYTES;
+#ifdef MRB_DIAG_HALFB      // timing experiment only (wrong results): what would half the weight bytes per SM buy?
+                    mbar_expect_tx(full_bar(s), b_bytes);
+                    bulk_g2s(dst, img + (size_t)c * 2 * b_bytes, b_bytes / 2, full_bar(s));
+                    bulk_g2s(dst + b_bytes, img + (size_t)c * 2 * b_bytes + b_bytes, b_bytes / 2, full_bar(s));
+#else
                     mbar_expect_tx(full_bar(s), 2 * b_bytes);
                     bulk_g2s(dst, img + (size_t)c * 2 * b_bytes, b_bytes, full_bar(s));
                     bulk_g2s(dst + b_bytes, img + (size_t)c * 2 * b_bytes + b_bytes, b_bytes, full_bar(s));
+#endif
                 }
             }
         }
