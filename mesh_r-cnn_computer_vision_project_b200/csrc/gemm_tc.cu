@@ -19,6 +19,8 @@
 //   warp 16     lane 0 issues tcgen05.mma (kind::tf32, M=128, N=NT, K=8), tcgen05.commit frees the stage / signals the
 //               epilogue; the whole warp owns the TMEM allocation
 //   warp 17     lane 0 streams the packed weight chunk with cp.async.bulk (TMA bulk copy) onto the stage's mbarrier
+#include <cuda.h>
+#include <string.h>
 #include "common.cuh"
 #include "../../include/meshrcnn_b200.h"
 
@@ -120,6 +122,7 @@ struct Params {
     long long img_tile_stride;       // bytes between the images of consecutive N tiles
     float* C;
     int ldc;
+    int tma_store;                   // cmap describes C: the epilogue writes 32 x 32 blocks with TMA tensor stores
 };
 
 constexpr int PROD_WARPS = 8;        // A producer warps, 16 rows of the 128-row tile each
@@ -153,7 +156,7 @@ __device__ int g_tl_n[4];
 
 // Persistent: grid = min(#tiles, #SMs); every role loops over the CTA's tiles with pipeline state that carries across
 // tiles, so global-load latency, tensor work and the C write-back of consecutive tiles overlap on one SM.
-__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p, const __grid_constant__ CUtensorMap cmap) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int STAGES = p.stages, STAGE_BYTES = p.stage_bytes;
@@ -322,6 +325,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
         const int ew = warp & 3;                       // TMEM lane quadrant (PROD_WARPS is a multiple of 4)
         const int half = (warp - PROD_WARPS) >> 2;     // 0 | 1
         float* stage_t = epi + (warp - PROD_WARPS) * (32 * 33);
+        float* stage_tma = epi + (warp - PROD_WARPS) * (32 * 32);      // 4096-byte tiles (the ring keeps epi 1024-byte aligned)
         const bool aligned = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
         const int nblk = (NT + 31) / 32;
         const int blk_beg = half * ((nblk + 1) / 2), blk_end = half ? nblk : (nblk + 1) / 2;
@@ -370,7 +374,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
 #ifdef MRB_DIAG_NOEPI      // timing experiment only: the epilogue ends after the TMEM reads (no transpose, no stores)
                 if (acc[0] != 1.2345e-33f) continue;
 #endif
-                if (aligned && c0 + 32 <= NT && colbase + 32 <= p.N) {
+                if (p.tma_store) {
+                    // Each thread holds 32 columns of ONE row.  The block is written into a SWIZZLE_128B shared-memory tile
+                    // (16-byte chunk q of row r at chunk q ^ (r & 7): conflict free) and handed to the TMA unit, which writes
+                    // the 32 x 32 block to C (or adds it, for K segments after the first) and clips the rows beyond M; the warp
+                    // only waits until the tile has been READ before it refills it.
+                    float4* st4 = reinterpret_cast<float4*>(stage_tma);        // 32 rows x 8 chunks of 16 bytes, 1024-byte aligned
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        st4[lane * 8 + (q ^ (lane & 7))] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+                    if (c0 + 32 <= NT && colbase + 32 <= p.N) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (warp == PROD_WARPS && lane == 0) TL(1, 44);
+#ifndef MRB_DIAG_NOSTORE
+                        if (lane == 0) {
+                            const uint32_t src = smem_u32(stage_tma);
+                            const int row0 = m0 + ew * 32;
+                            if (p.accumulate)
+                                asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&cmap),
+                                             "r"(src), "r"(colbase), "r"(row0)
+                                             : "memory");
+                            else
+                                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&cmap),
+                                             "r"(src), "r"(colbase), "r"(row0)
+                                             : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+#endif
+                    } else {
+                        // trailing partial column block (N % 32 != 0): the tensor store clips only at 16-byte granularity, so the
+                        // block is written from the same tile with guarded, coalesced scalar stores (lane = column)
+                        __syncwarp();
+                        const int col = colbase + lane;
+                        if (c0 + lane < NT && col < p.N) {
+                            const float* tile = stage_tma;
+                            const int rmax = min(32, p.M - (m0 + ew * 32));
+                            float* dst = p.C + (size_t)(m0 + ew * 32) * p.ldc + col;
+                            for (int r = 0; r < rmax; ++r) {
+                                const float v = tile[r * 32 + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3))];
+                                dst[(size_t)r * p.ldc] = v + (p.accumulate ? dst[(size_t)r * p.ldc] : 0.f);
+                            }
+                        }
+                    }
+                    if (warp == PROD_WARPS && lane == 0) TL(1, 45);
+                } else if (aligned && c0 + 32 <= NT && colbase + 32 <= p.N) {
                     // Each thread holds 32 columns of ONE row; storing them directly would touch 32 different 128-byte lines
                     // per instruction.  The block goes through a swizzled (conflict-free) shared-memory tile instead, so
                     // that every st.global.v4 instruction writes four complete 128-byte row segments.
@@ -423,6 +473,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p) {
                 if (lane == 0) mbar_arrive(tempty_bar(ab));
             }
         }
+        if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all tensor stores of this warp done
     } else if (warp == PROD_WARPS + EPI_WARPS) {
         // ===== MMA issuer ========================================================================================
         if (lane == 0) {
@@ -868,6 +919,39 @@ extern "C" int mrb_gemm_tc_pack_graphconv(const float* w0, const float* w1, int 
     return check_launch("gemm_tc_pack_graphconv");
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup: the library keeps no link-time dependency on
+// libcuda (it must load on machines without a driver, e.g. for the symbol checks of the CPU test suite).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static std::atomic<void*> cached{nullptr};
+    void* f = cached.load(std::memory_order_acquire);
+    if (!f) {
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        cached.store(f, std::memory_order_release);
+    }
+    return (EncodeTiledFn)f;
+}
+
+// 2-D fp32 tensor map of C (M rows of ldc floats, N columns used) with 32 x 32 boxes in the SWIZZLE_128B shared-memory layout
+static bool make_c_map(CUtensorMap* map, float* C, int M, int N, int ldc) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    const cuuint64_t strides[1] = {(cuuint64_t)ldc * 4};
+    const cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, C, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+#ifndef MRB_TC_TMA_STORE
+#define MRB_TC_TMA_STORE 1
+#endif
+
 static int launch_gemm_tc(const float* A, int lda, int M, int K, const void* image, int N, float* C, int ldc, int accumulate,
                           void* stream_, const char* what) {
     MRB_REQUIRE(A && image && C, "%s: null pointer", what);
@@ -883,6 +967,10 @@ static int launch_gemm_tc(const float* A, int lda, int M, int K, const void* ima
     // epilogue adds into C with ordinary fp32 rounding.
     const int SEG = 32;
     const size_t b_bytes = (size_t)pl.NT * BK * 4;
+    alignas(64) CUtensorMap cmap;
+    memset(&cmap, 0, sizeof(cmap));
+    const bool c_aligned = (ldc % 4 == 0) && (((uintptr_t)C & 15) == 0);
+    const bool tma_store = MRB_TC_TMA_STORE && c_aligned && make_c_map(&cmap, C, M, N, ldc);
     for (int c0 = 0; c0 < pl.nchunks; c0 += SEG) {
         const int nch = min(SEG, pl.nchunks - c0);
         Params p;
@@ -902,10 +990,10 @@ static int launch_gemm_tc(const float* A, int lda, int M, int K, const void* ima
         p.mtiles = ceil_div(M, BM);
         p.ntiles = pl.ntiles;
         p.accumulate = (c0 > 0) || accumulate;
-        p.C = C; p.ldc = ldc;
+        p.C = C; p.ldc = ldc; p.tma_store = tma_store;
         p.stages = pl.stages; p.stage_bytes = pl.stage_bytes;
         const int grid = min(p.mtiles * p.ntiles, kNumSMs);
-        k_gemm_tc<<<grid, TC_THREADS, pl.stages * pl.stage_bytes + EPI_BYTES + 1024 + 256, (cudaStream_t)stream_>>>(p);
+        k_gemm_tc<<<grid, TC_THREADS, pl.stages * pl.stage_bytes + EPI_BYTES + 1024 + 256, (cudaStream_t)stream_>>>(p, cmap);
     }
     return check_launch(what);
 }
