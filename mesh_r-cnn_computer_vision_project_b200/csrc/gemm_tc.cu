@@ -127,8 +127,10 @@ struct Params {
 
 constexpr int PROD_WARPS = 8;        // A producer warps, 16 rows of the 128-row tile each
 constexpr int PROD_ROWS = BM / PROD_WARPS;
+// (measured with the TMA-store epilogue, K=128->256 / 256->128 / 256->256 at 206 k rows: 1: 100.9 / 141.9 / 164.0 us, 2: 100.0 /
+//  142.2 / 161.7, 3: 90.4 / 131.9 / 146.1, 4 (spills): 107.4 / 163.3 / 182.6)
 #ifndef MRB_TC_PREFETCH
-#define MRB_TC_PREFETCH 2
+#define MRB_TC_PREFETCH 3
 #endif
 constexpr int PREFETCH = MRB_TC_PREFETCH;   // A chunks in flight per producer thread (registers)
 // Diagnostic builds (scripts/variants.sh gemm_tc.cu ...): -DMRB_DIAG_NOLOAD (producers skip the global loads), -DMRB_DIAG_NOMMA
@@ -240,13 +242,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p, const __gri
                 for (int d = 0; d < PREFETCH; ++d) {
                     const int it = it0 + d;
                     if (it < total_its) {
+                        // Split into tf32 hi / lo BEFORE waiting for the stage (the values sit in registers anyway) and re-issue the
+                        // registers' next global loads right away: after the wait only the 8 shared-memory stores remain on the
+                        // stage's turn-around path.
                         const int s = it % STAGES, use = it / STAGES;
-                        if (use > 0) mbar_wait(empty_bar(s), (use - 1) & 1);
-                        if (threadIdx.x == 0) TL(0, 50);
-                        unsigned char* a_hi = smem + s * STAGE_BYTES;
-                        unsigned char* a_lo = a_hi + A_BYTES;
                         const int m0 = ((blockIdx.x + (it / p.nchunks) * gridDim.x) / p.ntiles) * BM;
                         const int kleft = p.K - ((it % p.nchunks) * BK + kc * 4);   // valid columns of this 16-byte chunk
+                        float4 hi[PROD_ROWS / 4], lo[PROD_ROWS / 4];
 #pragma unroll
                         for (int i = 0; i < PROD_ROWS / 4; ++i) {
                             float4 x = v[d][i];
@@ -255,20 +257,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(Params p, const __gri
                             x.y = (rin && kleft > 1) ? x.y : 0.f;
                             x.z = (rin && kleft > 2) ? x.z : 0.f;
                             x.w = (rin && kleft > 3) ? x.w : 0.f;
-                            float4 hi, lo;
-                            hi.x = tf32_rna(x.x); hi.y = tf32_rna(x.y); hi.z = tf32_rna(x.z); hi.w = tf32_rna(x.w);
-                            lo.x = tf32_rna(x.x - hi.x); lo.y = tf32_rna(x.y - hi.y); lo.z = tf32_rna(x.z - hi.z);
-                            lo.w = tf32_rna(x.w - hi.w);
+                            hi[i].x = tf32_rna(x.x); hi[i].y = tf32_rna(x.y); hi[i].z = tf32_rna(x.z); hi[i].w = tf32_rna(x.w);
+                            lo[i].x = tf32_rna(x.x - hi[i].x); lo[i].y = tf32_rna(x.y - hi[i].y); lo[i].z = tf32_rna(x.z - hi[i].z);
+                            lo[i].w = tf32_rna(x.w - hi[i].w);
+                        }
+                        if (it + PREFETCH < total_its) load_it(it + PREFETCH, v[d]);
+                        if (use > 0) mbar_wait(empty_bar(s), (use - 1) & 1);
+                        if (threadIdx.x == 0) TL(0, 50);
+                        unsigned char* a_hi = smem + s * STAGE_BYTES;
+                        unsigned char* a_lo = a_hi + A_BYTES;
+#pragma unroll
+                        for (int i = 0; i < PROD_ROWS / 4; ++i) {
                             const int row = r0 + 4 * i + rsub;
                             const int off = (row >> 3) * 1024 + (row & 7) * 128 + (((kc ^ (row & 7)) & 7) << 4);
-                            *reinterpret_cast<float4*>(a_hi + off) = hi;
-                            *reinterpret_cast<float4*>(a_lo + off) = lo;
+                            *reinterpret_cast<float4*>(a_hi + off) = hi[i];
+                            *reinterpret_cast<float4*>(a_lo + off) = lo[i];
                         }
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         __syncwarp();
                         if (lane == 0) mbar_arrive(full_bar(s));
                         if (threadIdx.x == 0) TL(0, 51);
-                        if (it + PREFETCH < total_its) load_it(it + PREFETCH, v[d]);
                     }
                 }
             }
