@@ -11,11 +11,13 @@
 // C written once, and the weight image (<= 0.8 MB) streams from L2.
 //
 // Persistent CTAs (one per SM) loop over 128-row M tiles x N tiles (<= 256 columns).  Warp roles (576 threads):
-//   warps 0-7   A producers: coalesced fp32 loads of the A chunk (128 x 32), 2 chunks in flight per thread, hi/lo split,
-//               swizzled st.shared, fence.proxy.async, mbarrier arrive
-//   warps 8-15  epilogue: tcgen05.ld (TMEM lane quadrant = warp % 4, column half = warp / 12) -> st.global.v4 for aligned C
-//               rows, shared-memory transpose otherwise; the TMEM accumulator is double buffered, so tile j's write-back
-//               overlaps tile j+1's MMAs
+//   warps 0-7   A producers: coalesced fp32 loads of the A chunk (128 x 32), 3 chunks in flight per thread; the hi/lo split
+//               and the next loads are issued BEFORE the wait for the stage, after it only swizzled st.shared,
+//               fence.proxy.async, mbarrier arrive
+//   warps 8-15  epilogue: tcgen05.ld (TMEM lane quadrant = warp % 4, column half = warp / 12) -> SWIZZLE_128B shared-memory
+//               tile -> TMA tensor store of the 32 x 32 block (cp.async.bulk.tensor, or cp.reduce...add for K segments) when
+//               C rows are 16-byte aligned, guarded scalar stores otherwise; the TMEM accumulator is double buffered, so
+//               tile j's write-back overlaps tile j+1's MMAs
 //   warp 16     lane 0 issues tcgen05.mma (kind::tf32, M=128, N=NT, K=8), tcgen05.commit frees the stage / signals the
 //               epilogue; the whole warp owns the TMEM allocation
 //   warp 17     lane 0 streams the packed weight chunk with cp.async.bulk (TMA bulk copy) onto the stage's mbarrier
@@ -135,7 +137,8 @@ constexpr int PROD_ROWS = BM / PROD_WARPS;
 constexpr int PREFETCH = MRB_TC_PREFETCH;   // A chunks in flight per producer thread (registers)
 // Diagnostic builds (scripts/variants.sh gemm_tc.cu ...): -DMRB_DIAG_NOLOAD (producers skip the global loads), -DMRB_DIAG_NOMMA
 // (the issuer skips the MMAs), -DMRB_DIAG_NOSTORE (the epilogue skips the C stores), -DMRB_DIAG_NOEPI (the epilogue stops after
-// its TMEM reads), -DMRB_DIAG_HALFB (half the weight bytes per chunk) isolate the legs of the pipeline (timing only).
+// its TMEM reads), -DMRB_DIAG_HALFB (half the weight bytes per chunk) isolate the legs of the pipeline (timing only);
+// -DMRB_DIAG_TN_NOLOAD / _NOEPI / _NOMMA do the same for the weight-gradient kernel.  Results: profiles/r02/gemm_tc_pipeline_legs.log.
 constexpr int EPI_WARPS = 8;         // epilogue warps: TMEM lane quadrant = warp % 4, column half = (warp - PROD_WARPS) / 4
 constexpr int TC_THREADS = (PROD_WARPS + EPI_WARPS + 2) * 32;   // producers | epilogue warps | MMA issuer | weight TMA
 constexpr int EPI_BYTES = EPI_WARPS * 32 * 33 * 4;
@@ -741,10 +744,18 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tn(ParamsTN p) {
                         if (m < ntail) xtail[t * TN_TAIL_MAX + m] = __ldg(p.Xtail + (size_t)v * p.ld_tail + m);
 #pragma unroll
                     for (int mb = 0; mb < 4; ++mb)
+#ifdef MRB_DIAG_TN_NOLOAD
+                        x[mb * 4 + t] = (float)(v + mb);
+#else
                         x[mb * 4 + t] = __ldg(p.X + (size_t)v * p.ldx + min(i0 + mb * 32 + lane, p.Kin - 1));
+#endif
 #pragma unroll
                     for (int nb = 0; nb < NBMAX; ++nb)
+#ifdef MRB_DIAG_TN_NOLOAD
+                        if (nb * 32 < NT) g[nb * 4 + t] = (float)(v - nb);
+#else
                         if (nb * 32 < NT) g[nb * 4 + t] = __ldg(p.G + (size_t)v * p.ldg + min(nb * 32 + lane, NT - 1));
+#endif
                 }
             };
             // nvalid: how many of the 4 vertices of this 16-byte k chunk exist (the rest is zero padding)
@@ -813,7 +824,11 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tn(ParamsTN p) {
                 uint32_t v[32];
                 tmem_ld32(tmem_d + ((uint32_t)(ew * 32) << 16) + (uint32_t)c0, v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#ifdef MRB_DIAG_TN_NOEPI
+                if (i < p.Kin && __uint_as_float(v[0]) == 1.2345e-33f) {
+#else
                 if (i < p.Kin) {
+#endif
                     float* dst = (c0 < p.n_split) ? p.C0 + (size_t)i * p.ldc + c0 : p.C1 + (size_t)i * p.ldc + (c0 - p.n_split);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
@@ -858,9 +873,11 @@ __global__ void __launch_bounds__(TN_THREADS, 1) k_gemm_tn(ParamsTN p) {
                 for (int kk = 0; kk < BK / 8; ++kk) {
                     const uint64_t dah = umma_desc(a_hi + kk * 32), dal = umma_desc(a_lo + kk * 32);
                     const uint64_t dbh = umma_desc(b_hi + kk * 32), dbl = umma_desc(b_lo + kk * 32);
+#ifndef MRB_DIAG_TN_NOMMA
                     umma_tf32(tmem_d, dal, dbh, idesc, (c | kk) != 0);
                     umma_tf32(tmem_d, dah, dbl, idesc, 1);
                     umma_tf32(tmem_d, dah, dbh, idesc, 1);
+#endif
                 }
                 umma_commit(empty_bar(s));
             }
