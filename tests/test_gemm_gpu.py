@@ -27,9 +27,11 @@ def _check(M, K, N, lda_pad=0, ldc_pad=0, split=None, transposed_src=False, seed
         w0d, w1d = w0.cuda(), w1.cuda()
         img = F_.tc_pack(w0d, w1d, 1, K // 2, 2, K // 2, K, N)
     ad = a_full.cuda()
-    c = torch.full((M, N + ldc_pad), -7.0, device="cuda")
+    c_all = torch.full((M + 40, N + ldc_pad), -7.0, device="cuda")     # 40 guard rows behind the matrix
+    c = c_all[:M]
     F_.tc_gemm(_lib.ptr(ad), K + lda_pad, M, K, img, N, _lib.ptr(c), N + ldc_pad)
     torch.cuda.synchronize()
+    assert bool((c_all[M:] == -7.0).all())                 # the (TMA) stores of the last, partial row tile are clipped at M
     want = a.double() @ wl.double()
     got = c[:, :N].cpu().double()
     scale = float(want.abs().max())
