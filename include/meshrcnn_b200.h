@@ -121,6 +121,11 @@ int mrb_gemm_tc_pack(const float* src0, const float* src1, long long stride_k, l
  * (mrb_gemm_tc_image_bytes(2D, K) bytes). */
 int mrb_gemm_tc_pack_graphconv(const float* w0, const float* w1, int K, int D, void* image_fwd, void* image_bwd,
                                void* stream);
+/* The same for n (weight block, dimension) sets in ONE launch: entry i packs the forward image of [w0[i] | w1[i]] (K[i] x
+ * 2 D[i], row stride D[i]) into image_fwd[i] and, unless image_bwd[i] is NULL, the input-gradient image into image_bwd[i].
+ * The arrays live in host memory (all dense GraphConv blocks of a forward pass: 11 launches become one). */
+int mrb_gemm_tc_pack_graphconv_batch(int n, const void* const* w0, const void* const* w1, const int* K, const int* D,
+                                     void* const* image_fwd, void* const* image_bwd, void* stream);
 int mrb_gemm_tc(const float* A, int lda, int M, int K, const void* image, int N, float* C, int ldc, void* stream);
 /* Weight gradients on the same tensor-core path: C[Kin x N] += X^T (V x Kin) * G (V x N), reduced over the V vertices
  * (split over CTAs, fp32 vector reductions into C -- the caller zero-fills C).  Columns [0, n_split) go to C0 and

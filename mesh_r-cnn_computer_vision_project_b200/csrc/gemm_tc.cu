@@ -611,6 +611,19 @@ __global__ void k_pack_b2(PackParams a, PackParams b, long long total_a) {
     else pack_element(b, t - total_a);
 }
 
+// many images in one launch (all dense GraphConv blocks of a forward pass): block -> entry through a prefix table
+constexpr int PACK_BATCH_MAX = 32;
+struct PackBatch {
+    PackParams e[PACK_BATCH_MAX];
+    unsigned first_block[PACK_BATCH_MAX + 1];
+    int n;
+};
+__global__ void __launch_bounds__(256) k_pack_batch(const __grid_constant__ PackBatch b) {
+    int i = 0;
+    while (i + 1 < b.n && blockIdx.x >= b.first_block[i + 1]) ++i;
+    pack_element(b.e[i], (long long)(blockIdx.x - b.first_block[i]) * blockDim.x + threadIdx.x);
+}
+
 struct Plan {
     int NT, ntiles, nchunks, tmem_cols, nacc;
     int stages, stage_bytes;
@@ -942,6 +955,48 @@ extern "C" int mrb_gemm_tc_pack_graphconv(const float* w0, const float* w1, int 
     const long long ta = (long long)pf.ntiles * pf.nchunks * pf.NT * BK, tb = (long long)pb.ntiles * pb.nchunks * pb.NT * BK;
     k_pack_b2<<<(unsigned)ceil_div64(ta + tb, 256), 256, 0, (cudaStream_t)stream_>>>(a, b, ta);
     return check_launch("gemm_tc_pack_graphconv");
+}
+
+extern "C" int mrb_gemm_tc_pack_graphconv_batch(int n, const void* const* w0, const void* const* w1, const int* K, const int* D,
+                                                void* const* image_fwd, void* const* image_bwd, void* stream_) {
+    MRB_REQUIRE(n >= 0 && (n == 0 || (w0 && w1 && K && D && image_fwd && image_bwd)), "gemm_tc_pack_graphconv_batch: bad arguments");
+    PackBatch b;
+    b.n = 0;
+    unsigned blocks = 0;
+    auto flush = [&]() {
+        if (b.n == 0) return;
+        b.first_block[b.n] = blocks;
+        k_pack_batch<<<blocks, 256, 0, (cudaStream_t)stream_>>>(b);
+        b.n = 0;
+        blocks = 0;
+    };
+    auto add = [&](const PackParams& e, const Plan& pl) {
+        if (b.n == PACK_BATCH_MAX) flush();
+        b.e[b.n] = e;
+        b.first_block[b.n] = blocks;
+        blocks += (unsigned)ceil_div64((long long)pl.ntiles * pl.nchunks * pl.NT * BK, 256);
+        ++b.n;
+    };
+    for (int i = 0; i < n; ++i) {
+        MRB_REQUIRE(w0[i] && w1[i] && image_fwd[i] && K[i] > 0 && D[i] > 0, "gemm_tc_pack_graphconv_batch: bad entry %d", i);
+        MRB_REQUIRE((((uintptr_t)image_fwd[i] | (uintptr_t)image_bwd[i]) & 15) == 0,
+                    "gemm_tc_pack_graphconv_batch: images must be 16-byte aligned");
+        // same operands as mrb_gemm_tc_pack_graphconv: forward [W0 | W1] (K x 2D), input gradient [W0 | W1]^T (2D x K)
+        const Plan pf = make_plan(K[i], 2 * D[i]);
+        PackParams a;
+        a.src0 = (const float*)w0[i]; a.src1 = (const float*)w1[i]; a.sk = D[i]; a.sn = 1; a.split_axis = 1; a.split_at = D[i];
+        a.K = K[i]; a.N = 2 * D[i]; a.NT = pf.NT; a.nchunks = pf.nchunks; a.ntiles = pf.ntiles; a.image = (unsigned char*)image_fwd[i];
+        add(a, pf);
+        if (image_bwd[i]) {
+            const Plan pb = make_plan(2 * D[i], K[i]);
+            PackParams c;
+            c.src0 = (const float*)w0[i]; c.src1 = (const float*)w1[i]; c.sk = 1; c.sn = D[i]; c.split_axis = 2; c.split_at = D[i];
+            c.K = 2 * D[i]; c.N = K[i]; c.NT = pb.NT; c.nchunks = pb.nchunks; c.ntiles = pb.ntiles; c.image = (unsigned char*)image_bwd[i];
+            add(c, pb);
+        }
+    }
+    flush();
+    return check_launch("gemm_tc_pack_graphconv_batch");
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point lookup: the library keeps no link-time dependency on

@@ -459,6 +459,83 @@ class TexelTerm:
                   self.size, _lib.ptr(self.texrow))
 
 
+class PackPlan:
+    """Weight images of all dense GraphConv blocks of ONE forward pass, packed by a single launch.
+
+    Every block of a pass asks for its images through ``take``; what it asked for is remembered, and the next ``begin`` (the
+    start of the next pass through the same modules) packs that whole list at once (``mrb_gemm_tc_pack_graphconv_batch``: one
+    launch instead of one per block).  Nothing is carried over between passes -- the images are re-packed from the current
+    weights at every ``begin`` -- and a block the list does not hold (first pass, changed structure, re-allocated weights)
+    simply packs its own image as before."""
+
+    def __init__(self):
+        self._asked = {}       # key -> (w0, w1, row, K, D, want_bwd), insertion order = call order of the last pass
+        self._images = {}      # key -> (img, img_bwd | None) of the current pass
+
+    @staticmethod
+    def _key(w0, w1, row, K, D):
+        return (w0.data_ptr(), w1.data_ptr(), row, K, D)
+
+    def begin(self):
+        reqs = [r for r in self._asked.values() if r[0].is_cuda]
+        self._asked = {}
+        self._images = {}
+        if not reqs:
+            return
+        lib = _lib.load()
+        dev = reqs[0][0].device
+        sizes, total = [], 0
+        for (w0, w1, row, K, D, want_bwd) in reqs:
+            nf = (lib.mrb_gemm_tc_image_bytes(K, 2 * D) + 255) & ~255
+            nb = ((lib.mrb_gemm_tc_image_bytes(2 * D, K) + 255) & ~255) if want_bwd else 0
+            sizes.append((total, nf, nb))
+            total += nf + nb
+        buf = torch.empty(total, dtype=torch.uint8, device=dev)
+        base = buf.data_ptr()
+        n = len(reqs)
+        VP, IA = ctypes.c_void_p * n, ctypes.c_int * n
+        w0a = VP(*[r[0].data_ptr() + 4 * r[2] * r[4] for r in reqs])
+        w1a = VP(*[r[1].data_ptr() + 4 * r[2] * r[4] for r in reqs])
+        fa = VP(*[base + o for (o, nf, nb) in sizes])
+        ba = VP(*[(base + o + nf) if nb else None for (o, nf, nb) in sizes])
+        _lib.call("mrb_gemm_tc_pack_graphconv_batch", n, w0a, w1a, IA(*[r[3] for r in reqs]), IA(*[r[4] for r in reqs]), fa, ba)
+        for r, (o, nf, nb) in zip(reqs, sizes):
+            key = self._key(r[0], r[1], r[2], r[3], r[4])
+            self._images[key] = (buf[o:o + nf], buf[o + nf:o + nf + nb] if nb else None, r[0]._version, r[1]._version)
+
+    def take(self, w0, w1, row, K, D, want_bwd):
+        """(img, img_bwd) packed at ``begin`` for this block, or None; either way the block is on the list of the next pass."""
+        key = self._key(w0, w1, row, K, D)
+        self._asked[key] = (w0, w1, row, K, D, bool(want_bwd))
+        hit = self._images.get(key)
+        if hit is None or (want_bwd and hit[1] is None) or hit[2] != w0._version or hit[3] != w1._version:
+            return None
+        return hit[0], (hit[1] if want_bwd else None)
+
+
+_ACTIVE_PACK_PLAN = None
+
+
+class pack_plan:
+    """``with pack_plan(plan):`` -- the dense GraphConv blocks evaluated inside use (and feed) ``plan``."""
+
+    def __init__(self, plan: Optional[PackPlan]):
+        self.plan = plan
+
+    def __enter__(self):
+        global _ACTIVE_PACK_PLAN
+        self.prev = _ACTIVE_PACK_PLAN
+        _ACTIVE_PACK_PLAN = self.plan
+        if self.plan is not None:
+            self.plan.begin()
+        return self.plan
+
+    def __exit__(self, *exc):
+        global _ACTIVE_PACK_PLAN
+        _ACTIVE_PACK_PLAN = self.prev
+        return False
+
+
 def _project_block(a_ptr: int, lda: int, M: int, K: int, w0: Tensor, w1: Tensor, row: int, D: int, c_ptr: int, accumulate: bool,
                    want_bwd_image: bool):
     """C[M x 2D] (+)= A[M x K] @ [W0[row:row+K] | W1[row:row+K]].  Returns the operand image of the input gradient
@@ -467,6 +544,12 @@ def _project_block(a_ptr: int, lda: int, M: int, K: int, w0: Tensor, w1: Tensor,
     p0, p1 = w0.data_ptr() + 4 * row * D, w1.data_ptr() + 4 * row * D
     if _use_tc(K, 2 * D):
         lib = _lib.load()
+        want_bwd = bool(want_bwd_image and _use_tc(2 * D, K))
+        if _ACTIVE_PACK_PLAN is not None:
+            hit = _ACTIVE_PACK_PLAN.take(w0, w1, row, K, D, want_bwd)
+            if hit is not None:                         # packed with all the other blocks of this pass
+                _lib.call("mrb_gemm_tc_acc", a_ptr, lda, M, K, _lib.ptr(hit[0]), 2 * D, c_ptr, 2 * D, int(accumulate))
+                return hit[1]
         img = torch.empty(lib.mrb_gemm_tc_image_bytes(K, 2 * D), dtype=torch.uint8, device=dev)
         img_bwd = None
         if want_bwd_image and _use_tc(2 * D, K):

@@ -57,6 +57,7 @@ class RefinementHead(nn.Module):
         self.refineStages = nn.ModuleList(stages)
         self.overlap_losses = True          # training: per-stage losses on a second CUDA stream (see forward)
         self._loss_stream = None
+        self._pack_plan = None              # functional.PackPlan: the blocks' weight images of a pass in one launch
 
     def forward(self, voxel_probs: Tensor, feature_maps: Union[Tensor, List[Tensor]], image_sizes,
                 targets: Optional[MeshTargets] = None, mesh_index: Optional[List[int]] = None,
@@ -66,6 +67,13 @@ class RefinementHead(nn.Module):
         if self.training and targets is None:
             raise ValueError("In training mode, targets should be passed")
         mesh_index = [1 for _ in image_sizes] if mesh_index is None else mesh_index
+        from . import functional as F_
+        if self._pack_plan is None:
+            self._pack_plan = F_.PackPlan()
+        with F_.pack_plan(self._pack_plan if voxel_probs.is_cuda else None):      # one weight-packing launch per pass
+            return self._forward(voxel_probs, feature_maps, image_sizes, targets, mesh_index, loss_randomness, voxel_logits)
+
+    def _forward(self, voxel_probs, feature_maps, image_sizes, targets, mesh_index, loss_randomness, voxel_logits) -> dict:
         pos0, vertice_index, faces, face_index, adj_index = self.cubify(voxel_probs, from_logits=voxel_logits)
         positions = [pos0]
         feats = None
