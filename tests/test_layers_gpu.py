@@ -593,6 +593,48 @@ def test_graph_conv_parts_vs_oracle(lib, with_feat, with_tex, with_res):
         close(got[k], wv, what="parts %s" % k)
 
 
+def test_pack_plan_batches_weight_images_without_changing_results(lib):
+    """functional.PackPlan: the second pass through the same blocks packs all weight images with ONE launch, re-packs after
+    a weight update, and values / gradients are bit-identical to the per-block path."""
+    from meshrcnn_b200 import functional as F_, _lib
+    c = _parts_case(True, True)
+    sizes, mi = [(224, 224)] * c["B"], [1] * c["B"]
+    w0, w1 = c["w0"].cuda().requires_grad_(), c["w1"].cuda().requires_grad_()
+
+    def run(plan):
+        pos, feat, fmap = c["pos"].cuda().requires_grad_(), c["feat"].cuda().requires_grad_(), c["fmap"].cuda().requires_grad_()
+        w0.grad = w1.grad = None
+        calls = []
+        orig = _lib.call
+        _lib.call = lambda name, *a: (calls.append(name), orig(name, *a))[1]
+        try:
+            with F_.pack_plan(plan):
+                tex = F_.TexelTerm(fmap, pos, c["v_index"], sizes, mi)
+                out = F_.graph_conv_parts([("x", feat), ("pos", pos), ("tex", tex)], c["adj"], w0, w1, None)
+                (out * c["go"].cuda()).sum().backward()
+        finally:
+            _lib.call = orig
+        return [out.detach(), pos.grad, feat.grad, fmap.grad, w0.grad.clone(), w1.grad.clone()], calls
+
+    ref, calls0 = run(None)
+    plan = F_.PackPlan()
+    first, calls1 = run(plan)                      # nothing on the list yet: per-block packing, the blocks get recorded
+    second, calls2 = run(plan)                     # one batched launch
+    packs = lambda cs: [n for n in cs if "pack" in n]
+    assert packs(calls1) == packs(calls0) and len(packs(calls0)) == 2
+    assert packs(calls2) == ["mrb_gemm_tc_pack_graphconv_batch"]
+    assert torch.equal(ref[0], first[0]) and torch.equal(ref[0], second[0])          # forward values: bit-identical
+    for a, b, c_ in zip(ref[1:], first[1:], second[1:]):                             # gradients: atomic summation order only
+        scale = float(a.abs().max())
+        assert float((a - b).abs().max()) <= 2e-5 * scale and float((a - c_).abs().max()) <= 2e-5 * scale
+    with torch.no_grad():                          # an optimiser step: the next pass must pack the NEW weights
+        w0.mul_(0.5)
+    third, calls3 = run(plan)
+    fresh, _ = run(None)
+    assert packs(calls3) == ["mrb_gemm_tc_pack_graphconv_batch"]
+    assert torch.equal(third[0], fresh[0]) and not torch.equal(third[0], ref[0])
+
+
 def test_position_head_vs_oracle(lib):
     """pos + tanh([pos | x] W^T) (Pix3D), pos + tanh(x W^T) (ShapeNet): one kernel forward, fused backward."""
     from meshrcnn_b200 import functional as F_
