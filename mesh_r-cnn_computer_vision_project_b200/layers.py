@@ -289,7 +289,9 @@ class VertixRefinePix3D(nn.Module):
                 assert len(vertice_index) == len(image_sizes)
                 assert list(mesh_index) == [1 for _ in image_sizes]
             assert len(mesh_index) == len(image_sizes)
-            aligned = F_.TexelTerm(back_bone_features, vertex_positions, vertice_index, image_sizes, mesh_index)
+            # (the registered topology of a Cubify adjacency already holds the per-vertex mesh ids)
+            aligned = F_.TexelTerm(back_bone_features, vertex_positions, vertice_index, image_sizes, mesh_index,
+                                   topo=topology.lookup(vertex_adjacency, vertex_positions.shape[0]))
         else:
             aligned = self.vertAlign([back_bone_features], vertex_positions, vertice_index, image_sizes, mesh_index)
         x = _stage_input(vertex_positions, aligned, vertex_features, self.use_input_features)
