@@ -5,6 +5,7 @@ allocates its outputs with torch (device memory only) and launches hand-written 
 caller's current stream through ``_lib.call``.
 """
 import ctypes
+import threading
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -513,26 +514,24 @@ class PackPlan:
         return hit[0], (hit[1] if want_bwd else None)
 
 
-_ACTIVE_PACK_PLAN = None
+_PACK_TLS = threading.local()       # .plan: the PackPlan of the pass running on this thread (one thread per GPU is supported)
 
 
 class pack_plan:
-    """``with pack_plan(plan):`` -- the dense GraphConv blocks evaluated inside use (and feed) ``plan``."""
+    """``with pack_plan(plan):`` -- the dense GraphConv blocks evaluated inside (on this thread) use and feed ``plan``."""
 
     def __init__(self, plan: Optional[PackPlan]):
         self.plan = plan
 
     def __enter__(self):
-        global _ACTIVE_PACK_PLAN
-        self.prev = _ACTIVE_PACK_PLAN
-        _ACTIVE_PACK_PLAN = self.plan
+        self.prev = getattr(_PACK_TLS, "plan", None)
+        _PACK_TLS.plan = self.plan
         if self.plan is not None:
             self.plan.begin()
         return self.plan
 
     def __exit__(self, *exc):
-        global _ACTIVE_PACK_PLAN
-        _ACTIVE_PACK_PLAN = self.prev
+        _PACK_TLS.plan = self.prev
         return False
 
 
@@ -545,8 +544,9 @@ def _project_block(a_ptr: int, lda: int, M: int, K: int, w0: Tensor, w1: Tensor,
     if _use_tc(K, 2 * D):
         lib = _lib.load()
         want_bwd = bool(want_bwd_image and _use_tc(2 * D, K))
-        if _ACTIVE_PACK_PLAN is not None:
-            hit = _ACTIVE_PACK_PLAN.take(w0, w1, row, K, D, want_bwd)
+        plan = getattr(_PACK_TLS, "plan", None)
+        if plan is not None:
+            hit = plan.take(w0, w1, row, K, D, want_bwd)
             if hit is not None:                         # packed with all the other blocks of this pass
                 _lib.call("mrb_gemm_tc_acc", a_ptr, lda, M, K, _lib.ptr(hit[0]), 2 * D, c_ptr, 2 * D, int(accumulate))
                 return hit[1]
