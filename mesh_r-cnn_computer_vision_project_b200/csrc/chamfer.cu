@@ -337,7 +337,15 @@ __global__ void __launch_bounds__(THREADS) k_nn(const float4* __restrict__ a, co
 constexpr int GMAX = 32;                 // cells per axis (G^3 int counters must fit in shared memory)
 constexpr int GRID_MAX_POINTS = 65535;   // cell offsets are uint16
 constexpr int GRID_THREADS = 128;
-constexpr float GRID_C0 = 4.0f;          // first box sized for ~GRID_C0 * k points (measured best of 2..8 on B200)
+// (re-measured at the end of r2, scripts/variants.sh chamfer.cu "python scripts/time_knn.py 10 2": C0 3 / 4 / 5: 0.656 / 0.645 /
+//  0.672 ms; points per cell column (DENS) 8 / 12 / 16 / 24: 0.698 / 0.645 / 0.655 / 0.663 ms -- the defaults stay)
+#ifndef MRB_GRID_C0
+#define MRB_GRID_C0 4.0f
+#endif
+#ifndef MRB_GRID_DENS
+#define MRB_GRID_DENS 12.0
+#endif
+constexpr float GRID_C0 = MRB_GRID_C0;   // first box sized for ~GRID_C0 * k points (measured best of 2..8 on B200)
 constexpr int CS_STRIDE = GMAX * GMAX * GMAX + 2;
 
 struct __align__(16) GridHdr {
@@ -352,7 +360,7 @@ __device__ __forceinline__ int cell_of(float x, float lo, float inv, int G) {
 }
 
 static int grid_cells(int n) {
-    int g = (int)ceil(sqrt((double)n / 12.0));
+    int g = (int)ceil(sqrt((double)n / MRB_GRID_DENS));
     return g < 1 ? 1 : (g > GMAX ? GMAX : g);
 }
 
