@@ -5,6 +5,7 @@ allocates its outputs with torch (device memory only) and launches hand-written 
 caller's current stream through ``_lib.call``.
 """
 import ctypes
+import os
 import threading
 from typing import List, Optional, Sequence, Tuple
 
@@ -36,6 +37,20 @@ def _require_cuda(t: Tensor, what: str) -> None:
 # ----------------------------------------------------------------------------------------------------------
 # Cubify
 # ----------------------------------------------------------------------------------------------------------
+_PINNED = {}
+
+
+def _pinned_i64(n: int, device) -> Tensor:
+    """A reusable pinned int64 staging buffer per (thread, device, size) -- cudaHostAlloc per call would cost more than the copy."""
+    key = (threading.get_ident(), str(device), n)
+    buf = _PINNED.get(key)
+    if buf is None:
+        if len(_PINNED) > 64:
+            _PINNED.clear()
+        buf = _PINNED[key] = torch.empty(n, dtype=torch.int64).pin_memory()
+    return buf
+
+
 @torch.no_grad()
 def cubify(t: Tensor, threshold: float, from_logits: bool = False):
     """See ``layers.Cubify``.  Returns (verts, v_index, faces, f_index, adj, topology).  ``from_logits``: ``t`` holds the
@@ -55,7 +70,17 @@ def cubify(t: Tensor, threshold: float, from_logits: bool = False):
         meta = torch.empty(4 + 4 * B, dtype=torch.int64, device=dev)
         _lib.call("mrb_cubify_count", _lib.ptr(probs), B, Z, Y, X, float(threshold), int(bool(from_logits)), _lib.ptr(ws),
                   _lib.ptr(meta))
-        meta_h = meta.cpu()                      # the one unavoidable sync: the API returns Python lists
+        # The one unavoidable sync: the API returns Python lists.  The counters are copied into pinned memory asynchronously;
+        # work that does not depend on the mesh (the texel projections of the pass, functional.PackPlan) is launched behind
+        # the copy, so the device has something to do while this thread waits, allocates and issues the emit kernels.
+        meta_h = _pinned_i64(4 + 4 * B, dev)
+        meta_h.copy_(meta, non_blocking=True)
+        copied = torch.cuda.Event()
+        copied.record()
+        plan = getattr(_PACK_TLS, "plan", None)
+        if plan is not None:
+            plan.launch_early()
+        copied.synchronize()
         SV, SF, E = int(meta_h[0]), int(meta_h[1]), int(meta_h[2])
         if SF == 0:
             raise ValueError("empty grid")       # reference layers.py:434-435
@@ -460,6 +485,9 @@ class TexelTerm:
                   self.size, _lib.ptr(self.texrow))
 
 
+EARLY_TEXEL_PROJECTION = os.environ.get("MRB_EARLY_TEXEL", "1") != "0"     # A/B switch of PackPlan.begin's early projections
+
+
 class PackPlan:
     """Weight images of all dense GraphConv blocks of ONE forward pass, packed by a single launch.
 
@@ -472,15 +500,20 @@ class PackPlan:
     def __init__(self):
         self._asked = {}       # key -> (w0, w1, row, K, D, want_bwd), insertion order = call order of the last pass
         self._images = {}      # key -> (img, img_bwd | None) of the current pass
+        self._tex_asked = {}   # keys whose A operand is the texel-row matrix of the pass's feature map
+        self._tex_out = {}     # key -> (rows data_ptr, T) projected by ``launch_early``
+        self._pending = None   # (feature map, keys) of the projections ``launch_early`` will issue
 
     @staticmethod
     def _key(w0, w1, row, K, D):
         return (w0.data_ptr(), w1.data_ptr(), row, K, D)
 
-    def begin(self):
+    def begin(self, fmap: Optional[Tensor] = None):
+        """``fmap``: the pass's single feature map (Pix3D head).  The projections of its texel rows (one per stage) do not
+        depend on the mesh: they are queued here and launched by ``launch_early``."""
         reqs = [r for r in self._asked.values() if r[0].is_cuda]
-        self._asked = {}
-        self._images = {}
+        tex_keys = self._tex_asked
+        self._asked, self._images, self._tex_asked, self._tex_out, self._pending = {}, {}, {}, {}, None
         if not reqs:
             return
         lib = _lib.load()
@@ -503,15 +536,45 @@ class PackPlan:
         for r, (o, nf, nb) in zip(reqs, sizes):
             key = self._key(r[0], r[1], r[2], r[3], r[4])
             self._images[key] = (buf[o:o + nf], buf[o + nf:o + nf + nb] if nb else None, r[0]._version, r[1]._version)
+        if EARLY_TEXEL_PROJECTION and fmap is not None and fmap.is_cuda and fmap.dim() == 4 and tex_keys:
+            self._pending = (fmap, list(tex_keys))      # launched by ``launch_early`` (behind Cubify's count kernels)
 
-    def take(self, w0, w1, row, K, D, want_bwd):
-        """(img, img_bwd) packed at ``begin`` for this block, or None; either way the block is on the list of the next pass."""
+    def launch_early(self):
+        """The projections of the feature map's texel rows (one per stage): they do not depend on the mesh, so Cubify calls
+        this between its count kernels and the read-back of the counters -- the device works on them while the launching
+        thread is stalled."""
+        pending, self._pending = self._pending, None
+        if pending is None:
+            return
+        fmap, tex_keys = pending
+        rows = feature_rows(fmap)
+        R, C = rows.shape
+        for key in tex_keys:
+            hit = self._images.get(key)
+            if hit is None or key[3] != C:
+                continue
+            D = key[4]
+            T = torch.empty(R, 2 * D, dtype=torch.float32, device=rows.device)
+            _lib.call("mrb_gemm_tc_acc", _lib.ptr(rows), C, R, C, _lib.ptr(hit[0]), 2 * D, _lib.ptr(T), 2 * D, 0)
+            self._tex_out[key] = (rows.data_ptr(), T)
+
+    def take(self, w0, w1, row, K, D, want_bwd, a_ptr=None, texel_rows=False):
+        """(img, img_bwd, T | None) packed at ``begin`` for this block, or None; either way the block is on the list of the
+        next pass.  ``texel_rows``: the block multiplies the texel rows of the feature map (``a_ptr``); T is its product if it
+        was launched at ``begin`` from that very matrix."""
         key = self._key(w0, w1, row, K, D)
         self._asked[key] = (w0, w1, row, K, D, bool(want_bwd))
+        if texel_rows:
+            self._tex_asked[key] = True
         hit = self._images.get(key)
         if hit is None or (want_bwd and hit[1] is None) or hit[2] != w0._version or hit[3] != w1._version:
             return None
-        return hit[0], (hit[1] if want_bwd else None)
+        T = None
+        if texel_rows:
+            t = self._tex_out.pop(key, None)
+            if t is not None and t[0] == a_ptr:
+                T = t[1]
+        return hit[0], (hit[1] if want_bwd else None), T
 
 
 _PACK_TLS = threading.local()       # .plan: the PackPlan of the pass running on this thread (one thread per GPU is supported)
@@ -520,14 +583,14 @@ _PACK_TLS = threading.local()       # .plan: the PackPlan of the pass running on
 class pack_plan:
     """``with pack_plan(plan):`` -- the dense GraphConv blocks evaluated inside (on this thread) use and feed ``plan``."""
 
-    def __init__(self, plan: Optional[PackPlan]):
-        self.plan = plan
+    def __init__(self, plan: Optional[PackPlan], fmap: Optional[Tensor] = None):
+        self.plan, self.fmap = plan, fmap
 
     def __enter__(self):
         self.prev = getattr(_PACK_TLS, "plan", None)
         _PACK_TLS.plan = self.plan
         if self.plan is not None:
-            self.plan.begin()
+            self.plan.begin(self.fmap)
         return self.plan
 
     def __exit__(self, *exc):
@@ -536,7 +599,7 @@ class pack_plan:
 
 
 def _project_block(a_ptr: int, lda: int, M: int, K: int, w0: Tensor, w1: Tensor, row: int, D: int, c_ptr: int, accumulate: bool,
-                   want_bwd_image: bool):
+                   want_bwd_image: bool, texel_rows: bool = False, out: Optional[list] = None):
     """C[M x 2D] (+)= A[M x K] @ [W0[row:row+K] | W1[row:row+K]].  Returns the operand image of the input gradient
     ([gz | A^T gz] @ [W0 | W1]^T block) when it was packed in the same launch, else None."""
     dev = w0.device
@@ -546,9 +609,12 @@ def _project_block(a_ptr: int, lda: int, M: int, K: int, w0: Tensor, w1: Tensor,
         want_bwd = bool(want_bwd_image and _use_tc(2 * D, K))
         plan = getattr(_PACK_TLS, "plan", None)
         if plan is not None:
-            hit = plan.take(w0, w1, row, K, D, want_bwd)
+            hit = plan.take(w0, w1, row, K, D, want_bwd, a_ptr, texel_rows and lda == K and not accumulate)
             if hit is not None:                         # packed with all the other blocks of this pass
-                _lib.call("mrb_gemm_tc_acc", a_ptr, lda, M, K, _lib.ptr(hit[0]), 2 * D, c_ptr, 2 * D, int(accumulate))
+                if hit[2] is not None and out is not None:
+                    out.append(hit[2])                  # ... and already projected (texel rows): the caller takes this T
+                else:
+                    _lib.call("mrb_gemm_tc_acc", a_ptr, lda, M, K, _lib.ptr(hit[0]), 2 * D, c_ptr, 2 * D, int(accumulate))
                 return hit[1]
         img = torch.empty(lib.mrb_gemm_tc_image_bytes(K, 2 * D), dtype=torch.uint8, device=dev)
         img_bwd = None
@@ -610,8 +676,11 @@ class _GraphConvSplit(torch.autograd.Function):
         if tex is not None:
             R = tex.rows.shape[0]
             T = torch.empty(R, 2 * D, dtype=torch.float32, device=dev)
+            early = []
             tex_img_bwd = _project_block(_lib.ptr(tex.rows), tex.C, R, tex.C, w0, w1, tex_row, D, _lib.ptr(T), False,
-                                         ctx.needs_input_grad[5])
+                                         ctx.needs_input_grad[5], texel_rows=True, out=early)
+            if early:                                   # projected at the start of the pass (functional.PackPlan.begin)
+                T = early[0]
         out = torch.empty(n, D, dtype=torch.float32, device=dev)
         mask = torch.empty(n, (D + 31) // 32, dtype=torch.int32, device=dev)
         res = None if residual is None else _rows(residual)

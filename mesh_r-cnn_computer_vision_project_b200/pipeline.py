@@ -70,7 +70,8 @@ class RefinementHead(nn.Module):
         from . import functional as F_
         if self._pack_plan is None:
             self._pack_plan = F_.PackPlan()
-        with F_.pack_plan(self._pack_plan if voxel_probs.is_cuda else None):      # one weight-packing launch per pass
+        single_map = feature_maps if torch.is_tensor(feature_maps) else None
+        with F_.pack_plan(self._pack_plan if voxel_probs.is_cuda else None, single_map):   # one weight-packing launch per pass
             return self._forward(voxel_probs, feature_maps, image_sizes, targets, mesh_index, loss_randomness, voxel_logits)
 
     def _forward(self, voxel_probs, feature_maps, image_sizes, targets, mesh_index, loss_randomness, voxel_logits) -> dict:

@@ -608,7 +608,9 @@ def test_pack_plan_batches_weight_images_without_changing_results(lib):
         orig = _lib.call
         _lib.call = lambda name, *a: (calls.append(name), orig(name, *a))[1]
         try:
-            with F_.pack_plan(plan):
+            with F_.pack_plan(plan, fmap) as active:    # with the map: its texel rows can be projected ahead of the mesh
+                if active is not None:
+                    active.launch_early()               # (Cubify calls this between its count kernels and their read-back)
                 tex = F_.TexelTerm(fmap, pos, c["v_index"], sizes, mi)
                 out = F_.graph_conv_parts([("x", feat), ("pos", pos), ("tex", tex)], c["adj"], w0, w1, None)
                 (out * c["go"].cuda()).sum().backward()
@@ -623,6 +625,9 @@ def test_pack_plan_batches_weight_images_without_changing_results(lib):
     packs = lambda cs: [n for n in cs if "pack" in n]
     assert packs(calls1) == packs(calls0) and len(packs(calls0)) == 2
     assert packs(calls2) == ["mrb_gemm_tc_pack_graphconv_batch"]
+    first_gemm = lambda cs: [n for n in cs if n.startswith("mrb_gemm_tc_acc") or n.startswith("mrb_gc_") or "texrows" in n][0]
+    assert first_gemm(calls1) == "mrb_vert_align_texrows" and first_gemm(calls2) == "mrb_gemm_tc_acc"   # texel projection hoisted
+    assert calls2.count("mrb_gemm_tc_acc") == calls1.count("mrb_gemm_tc_acc")                           # ... not duplicated
     assert torch.equal(ref[0], first[0]) and torch.equal(ref[0], second[0])          # forward values: bit-identical
     for a, b, c_ in zip(ref[1:], first[1:], second[1:]):                             # gradients: atomic summation order only
         scale = float(a.abs().max())
