@@ -77,9 +77,7 @@ def cubify(t: Tensor, threshold: float, from_logits: bool = False):
         meta_h.copy_(meta, non_blocking=True)
         copied = torch.cuda.Event()
         copied.record()
-        plan = getattr(_PACK_TLS, "plan", None)
-        if plan is not None:
-            plan.launch_early()
+        run_deferred()
         copied.synchronize()
         SV, SF, E = int(meta_h[0]), int(meta_h[1]), int(meta_h[2])
         if SF == 0:
@@ -580,6 +578,26 @@ class PackPlan:
 _PACK_TLS = threading.local()       # .plan: the PackPlan of the pass running on this thread (one thread per GPU is supported)
 
 
+def defer_until_stall(fn) -> None:
+    """Registers mesh-independent device work of this thread's pass (a callable issuing launches on the current stream): it
+    runs at the next point where the launching thread has to wait for the device anyway (Cubify's counter read-back)."""
+    lst = getattr(_PACK_TLS, "deferred", None)
+    if lst is None:
+        lst = _PACK_TLS.deferred = []
+    lst.append(fn)
+
+
+def run_deferred() -> None:
+    plan = getattr(_PACK_TLS, "plan", None)
+    if plan is not None:
+        plan.launch_early()
+    lst = getattr(_PACK_TLS, "deferred", None)
+    if lst:
+        _PACK_TLS.deferred = []
+        for fn in lst:
+            fn()
+
+
 class pack_plan:
     """``with pack_plan(plan):`` -- the dense GraphConv blocks evaluated inside (on this thread) use and feed ``plan``."""
 
@@ -595,6 +613,7 @@ class pack_plan:
 
     def __exit__(self, *exc):
         _PACK_TLS.plan = self.prev
+        _PACK_TLS.deferred = []             # work registered for a stall that never came (an exception on the way) is dropped
         return False
 
 

@@ -32,12 +32,14 @@ def voxel_loss_with_logits(voxel_logits: Tensor, voxel_gts: Tensor, return_probs
 def batched_mesh_loss(vertex_positions_pred: List[Tensor], mesh_faces_pred: Tensor, pred_adjacency: Tensor,
                       vertices_per_sample_pred: List[int], faces_per_sample_pred: List[int], batch,
                       point_cloud_size: float = 10e3, num_neighbours_for_normal_loss: int = 10,
-                      randomness=None) -> Tuple[Tensor, Tensor, Tensor]:
+                      randomness=None, gt_clouds=None) -> Tuple[Tensor, Tensor, Tensor]:
     """Sum over the refinement stages of (chamfer, normal, edge) -- reference loss_functions.py:17-35.
-    ``randomness``: optional list (one entry per stage) of ``(rnd_pred, rnd_gt)`` injected draws, see ``mesh_loss``."""
+    ``randomness``: optional list (one entry per stage) of ``(rnd_pred, rnd_gt)`` injected draws, see ``mesh_loss``;
+    ``gt_clouds``: optional list of already drawn ground-truth samples, one per stage."""
     terms = [mesh_loss(pos, mesh_faces_pred, pred_adjacency, vertices_per_sample_pred, faces_per_sample_pred, batch,
                        point_cloud_size, num_neighbours_for_normal_loss,
-                       randomness=None if randomness is None else randomness[s])
+                       randomness=None if randomness is None else randomness[s],
+                       gt_cloud=None if gt_clouds is None else gt_clouds[s])
              for s, pos in enumerate(vertex_positions_pred)]
     return tuple(F_.weighted_scalar_sum([t[i] for t in terms]) for i in range(3))     # one launch per term (was 2 adds each)
 
@@ -45,8 +47,10 @@ def batched_mesh_loss(vertex_positions_pred: List[Tensor], mesh_faces_pred: Tens
 def mesh_loss(vertex_positions_pred: Tensor, mesh_faces_pred: Tensor, pred_adjacency: Tensor,
               vertices_per_sample_pred: List[int], faces_per_sample_pred: List[int], batch,
               point_cloud_size: float = 10e3, num_neighbours_for_normal_loss: int = 10,
-              randomness=None) -> Tuple[Tensor, Tensor, Tensor]:
+              randomness=None, gt_cloud: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor]:
     """(chamfer, normal, edge) of one stage -- reference loss_functions.py:40-74.
+    ``gt_cloud``: the stage's ground-truth sample if the caller already drew it (``sample_gt_cloud``; the refinement head
+    samples the static GT meshes ahead of the predicted mesh, with the seeds in the order of the lazy path).
 
     ``randomness = (rnd_pred, rnd_gt)`` with ``rnd_* = dict(u=|face_idx=, xi2=, xi1=)`` (B x n tensors) injects the
     sampling draws of the predicted / ground-truth clouds; default: fresh in-kernel Philox draws for both, the GT
@@ -59,15 +63,24 @@ def mesh_loss(vertex_positions_pred: Tensor, mesh_faces_pred: Tensor, pred_adjac
 
     cloud_pred, _ = F_.sample_points(vertex_positions_pred, mesh_faces_pred, vertices_per_sample_pred,
                                      faces_per_sample_pred, n, **rnd_pred)                          # :51-53
-    pos_gt, faces_gt = batch.meshes
     # :57-59 -- the GT cloud is re-sampled at every call like the reference; the area CDF of the static GT meshes is
     # computed once per batch object (device-resident cache, functional.cached_face_cdf)
-    cloud_gt, _ = F_.sample_points(pos_gt, faces_gt, batch.vertice_index, batch.face_index, n, cdf_owner=batch, **rnd_gt)
+    if gt_cloud is None:
+        gt_cloud = sample_gt_cloud(batch, n, **rnd_gt)
+    cloud_gt = gt_cloud
 
     # :62-66,141  (loss_p + loss_gt) / point_cloud_size as one scalar; :69-72  -(nd_p + nd_gt) / point_cloud_size likewise
     chamfer_loss, idx_p, idx_gt, knn_p, knn_gt = F_.chamfer_total(cloud_pred, cloud_gt, k, 1.0 / point_cloud_size)
     normal_loss = F_.normal_total(cloud_pred, cloud_gt, knn_p, knn_gt, idx_p, idx_gt, -1.0 / point_cloud_size)
     return chamfer_loss, normal_loss, edge_loss
+
+
+def sample_gt_cloud(batch, point_cloud_size: float = 10e3, **randomness) -> Tensor:
+    """B x n x 3 normalised surface sample of the ground-truth meshes of ``batch`` (reference loss_functions.py:57-59)."""
+    pos_gt, faces_gt = batch.meshes
+    cloud, _ = F_.sample_points(pos_gt, faces_gt, batch.vertice_index, batch.face_index, int(point_cloud_size), cdf_owner=batch,
+                                **randomness)
+    return cloud
 
 
 def batched_mesh_sampling(vertex_positions: Tensor, mesh_faces: Tensor, vertices_per_sample: List[int],

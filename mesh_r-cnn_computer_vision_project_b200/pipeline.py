@@ -4,6 +4,7 @@
 backbone / voxel branch upstream of it are out of scope and are replaced by the ``voxel_probs`` /
 ``feature_maps`` arguments.
 """
+import os
 from typing import List, Optional, Sequence, Tuple, Union
 
 import torch
@@ -11,7 +12,7 @@ import torch.nn as nn
 from torch import Tensor
 
 from .layers import Cubify, ResVertixRefineShapenet, VertixRefinePix3D, VertixRefineShapeNet
-from .loss_functions import batched_mesh_loss, mesh_loss
+from .loss_functions import batched_mesh_loss, mesh_loss, sample_gt_cloud
 
 
 class MeshTargets:
@@ -58,6 +59,7 @@ class RefinementHead(nn.Module):
         self.overlap_losses = True          # training: per-stage losses on a second CUDA stream (see forward)
         self._loss_stream = None
         self._pack_plan = None              # functional.PackPlan: the blocks' weight images of a pass in one launch
+        self.sample_gt_early = os.environ.get("MRB_EARLY_GT", "1") != "0"   # training: GT clouds of all stages drawn during Cubify's read-back stall
 
     def forward(self, voxel_probs: Tensor, feature_maps: Union[Tensor, List[Tensor]], image_sizes,
                 targets: Optional[MeshTargets] = None, mesh_index: Optional[List[int]] = None,
@@ -75,7 +77,22 @@ class RefinementHead(nn.Module):
             return self._forward(voxel_probs, feature_maps, image_sizes, targets, mesh_index, loss_randomness, voxel_logits)
 
     def _forward(self, voxel_probs, feature_maps, image_sizes, targets, mesh_index, loss_randomness, voxel_logits) -> dict:
+        from . import functional as F_
+        gt_clouds = None
+        if self.training and voxel_probs.is_cuda and loss_randomness is None and self.sample_gt_early:
+            # The ground-truth samples of the stages do not depend on the predicted mesh: they are drawn while the launching
+            # thread waits for Cubify's counters (functional.defer_until_stall).  The Philox seeds are taken from torch's
+            # generator here, in the order the lazy path would take them (stage by stage: predicted cloud, GT cloud), so the
+            # draws are the ones batched_mesh_loss(positions, ...) would make after the same torch.manual_seed.
+            n_stage = len(self.refineStages)
+            seeds = [F_._next_seed() for _ in range(2 * n_stage)]
+            loss_randomness = [({"seed": seeds[2 * s]}, {"seed": seeds[2 * s + 1]}) for s in range(n_stage)]
+            gt_clouds = []
+            F_.defer_until_stall(lambda: gt_clouds.extend(sample_gt_cloud(targets, **loss_randomness[s][1])
+                                                          for s in range(n_stage)))
         pos0, vertice_index, faces, face_index, adj_index = self.cubify(voxel_probs, from_logits=voxel_logits)
+        if gt_clouds is not None and len(gt_clouds) != len(self.refineStages):
+            gt_clouds = None                            # the hook did not run (a Cubify path without the stall): lazy sampling
         positions = [pos0]
         feats = None
         overlap = self.training and self.overlap_losses and voxel_probs.is_cuda
@@ -99,9 +116,12 @@ class RefinementHead(nn.Module):
                 # passes overlap the same way.  (Stream priorities -- stages high, losses low -- were measured: no gain.)
                 side.wait_stream(main)
                 new_pos.record_stream(side)
+                if gt_clouds is not None:
+                    gt_clouds[s].record_stream(side)
                 with torch.cuda.stream(side):
                     terms.append(mesh_loss(new_pos, faces, adj_index, vertice_index, face_index, targets,
-                                           randomness=None if loss_randomness is None else loss_randomness[s]))
+                                           randomness=None if loss_randomness is None else loss_randomness[s],
+                                           gt_cloud=None if gt_clouds is None else gt_clouds[s]))
         out = {}
         if self.training:
             if overlap:
@@ -113,7 +133,7 @@ class RefinementHead(nn.Module):
                 chamfer, normal, edge = (F_.weighted_scalar_sum([t[i] for t in terms]) for i in range(3))
             else:
                 chamfer, normal, edge = batched_mesh_loss(positions[1:], faces, adj_index, vertice_index, face_index,
-                                                          targets, randomness=loss_randomness)
+                                                          targets, randomness=loss_randomness, gt_clouds=gt_clouds)
             out.update({"chamfer_loss": chamfer, "edge_loss": edge, "normal_loss": normal})
         else:
             out.update({"vertex_positions": positions, "edge_index": adj_index, "face_index": face_index,
