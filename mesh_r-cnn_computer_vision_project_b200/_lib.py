@@ -79,8 +79,30 @@ def load():
             fn.argtypes = [_C[a] for a in args]
         if lib.mrb_version() != 100:
             raise RuntimeError("meshrcnn_b200: library/header version mismatch")
+        _bind_fast(lib)
         _lib = lib
     return _lib
+
+
+# Optional call shim (csrc/host/fastcall.c, built by meshrcnn_b200.build): entry points whose arguments are all pointers /
+# int / long long are called through a plain cast instead of libffi (ctypes spends 3-5 us per call on ~15 arguments, a step
+# makes ~150 calls).  Same library, same symbols; without the shim everything goes through ctypes.
+_FAST = {}            # name -> address of the entry point
+_fast_call = None
+
+
+def _bind_fast(lib):
+    global _fast_call
+    if os.environ.get("MRB_NO_FASTCALL", "0") == "1":
+        return
+    try:
+        from . import _fastcall
+    except ImportError:
+        return
+    for name, (ret, args) in SIGNATURES.items():
+        if ret == "i" and all(a in "pilL" for a in args):
+            _FAST[name] = ctypes.cast(getattr(lib, name), ctypes.c_void_p).value
+    _fast_call = _fastcall.call_ints
 
 
 def stream_ptr() -> int:
@@ -148,7 +170,16 @@ def call(name: str, *args):
     lib = load()
     launch_count += LAUNCHES.get(name, 1)
     if _timing is None:
-        check(getattr(lib, name)(*args, stream_ptr()), name)
+        addr = _FAST.get(name)
+        if addr is not None:
+            try:
+                rc = _fast_call(addr, args + (stream_ptr(),))
+            except TypeError:                  # an argument that is not an int / None (e.g. a ctypes array): let ctypes convert it
+                rc = getattr(lib, name)(*args, stream_ptr())
+        else:
+            rc = getattr(lib, name)(*args, stream_ptr())
+        if rc != 0:
+            check(rc, name)
         return
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()

@@ -6,9 +6,11 @@ nvcc-12.9 objects do not depend on the cu128 runtime bundled with torch.
 """
 import glob
 import os
+import platform
 import shutil
 import subprocess
 import sys
+import sysconfig
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -43,6 +45,7 @@ def needs_build() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
+        build_fastcall()
         return LIB
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
@@ -68,8 +71,29 @@ def build(force: bool = False, verbose: bool = False) -> str:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    build_fastcall(force)
     return LIB
+
+
+FASTCALL_SRC = os.path.join(CSRC, "host", "fastcall.c")
+FASTCALL = os.path.join(HERE, "_fastcall" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+
+
+def build_fastcall(force: bool = False):
+    """The optional host-side call shim (csrc/host/fastcall.c, plain C + the CPython API, gcc).  Returns its path, or None
+    if it cannot be built here (no compiler / no Python headers): meshrcnn_b200._lib then calls through ctypes only."""
+    if platform.machine() not in ("x86_64", "AMD64") or not sys.platform.startswith("linux"):
+        return None
+    if not force and os.path.exists(FASTCALL) and os.path.getmtime(FASTCALL) > os.path.getmtime(FASTCALL_SRC):
+        return FASTCALL
+    cc = os.environ.get("CC") or shutil.which("gcc") or shutil.which("cc")
+    inc = sysconfig.get_paths().get("include")
+    if not cc or not inc or not os.path.exists(os.path.join(inc, "Python.h")):
+        return None
+    r = subprocess.run([cc, "-O2", "-fPIC", "-shared", "-I", inc, FASTCALL_SRC, "-o", FASTCALL], capture_output=True, text=True)
+    return FASTCALL if r.returncode == 0 else None
 
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_fastcall(force="--force" in sys.argv))

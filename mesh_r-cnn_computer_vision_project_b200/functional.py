@@ -530,7 +530,8 @@ class PackPlan:
         w1a = VP(*[r[1].data_ptr() + 4 * r[2] * r[4] for r in reqs])
         fa = VP(*[base + o for (o, nf, nb) in sizes])
         ba = VP(*[(base + o + nf) if nb else None for (o, nf, nb) in sizes])
-        _lib.call("mrb_gemm_tc_pack_graphconv_batch", n, w0a, w1a, IA(*[r[3] for r in reqs]), IA(*[r[4] for r in reqs]), fa, ba)
+        Ka, Da = IA(*[r[3] for r in reqs]), IA(*[r[4] for r in reqs])
+        _lib.call("mrb_gemm_tc_pack_graphconv_batch", n, *(ctypes.addressof(x) for x in (w0a, w1a, Ka, Da, fa, ba)))
         for r, (o, nf, nb) in zip(reqs, sizes):
             key = self._key(r[0], r[1], r[2], r[3], r[4])
             self._images[key] = (buf[o:o + nf], buf[o + nf:o + nf + nb] if nb else None, r[0]._version, r[1]._version)
@@ -1365,7 +1366,7 @@ class _ScalarCombine(torch.autograd.Function):
         out = torch.empty(1, dtype=torch.float32, device=xc[0].device)
         ptrs = (ctypes.c_void_p * n)(*[x.data_ptr() for x in xc])
         w = (ctypes.c_float * n)(*[float(v) for v in weights])
-        _lib.call("mrb_scalar_combine", ptrs, w, n, _lib.ptr(out))
+        _lib.call("mrb_scalar_combine", ctypes.addressof(ptrs), ctypes.addressof(w), n, _lib.ptr(out))
         ctx.weights = tuple(float(v) for v in weights)
         return out[0]
 
@@ -1376,7 +1377,7 @@ class _ScalarCombine(torch.autograd.Function):
             return (None,) + (g,) * n                       # a plain sum: every term receives g itself, no kernel
         out = torch.empty(n, dtype=torch.float32, device=g.device)
         w = (ctypes.c_float * n)(*ctx.weights)
-        _lib.call("mrb_scalar_scatter", _lib.ptr(_f32c(g).reshape(1)), w, n, _lib.ptr(out))
+        _lib.call("mrb_scalar_scatter", _lib.ptr(_f32c(g).reshape(1)), ctypes.addressof(w), n, _lib.ptr(out))
         return (None,) + tuple(out[i] for i in range(n))
 
 

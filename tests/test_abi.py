@@ -65,3 +65,22 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
                 assert "/root/reference" not in text, f
+
+
+def test_fastcall_shim_calls_the_same_entry_points():
+    """csrc/host/fastcall.c: all-integer / pointer entry points called through a plain cast give the ctypes results (version,
+    error code + message of a rejected call -- no device work, so this runs without a GPU)."""
+    from meshrcnn_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    if _lib._fast_call is None:
+        pytest.skip("call shim not built on this platform")
+    addr = lambda name: ctypes.cast(getattr(lib, name), ctypes.c_void_p).value
+    assert _lib._fast_call(addr("mrb_version"), ()) == lib.mrb_version() == 100
+    assert "mrb_segment_ids" in _lib._FAST and "mrb_sgemm" not in _lib._FAST            # float arguments stay on ctypes
+    rc_fast = _lib._fast_call(_lib._FAST["mrb_segment_ids"], (None, 3, 7, None, None))   # null pointers: rejected before any launch
+    msg_fast = lib.mrb_last_error()
+    rc_ct = lib.mrb_segment_ids(None, 3, 7, None, None)
+    assert rc_fast == rc_ct != 0 and msg_fast == lib.mrb_last_error()
+    with pytest.raises(TypeError):
+        _lib._fast_call(addr("mrb_version"), (1.5,))
