@@ -484,6 +484,30 @@ class TexelTerm:
 
 
 EARLY_TEXEL_PROJECTION = os.environ.get("MRB_EARLY_TEXEL", "1") != "0"     # A/B switch of PackPlan.begin's early projections
+_IMAGE_BYTES = {}       # (K, N) -> mrb_gemm_tc_image_bytes(K, N) rounded up to 256
+
+
+def _image_bytes(K: int, N: int) -> int:
+    v = _IMAGE_BYTES.get((K, N))
+    if v is None:
+        v = _IMAGE_BYTES[(K, N)] = (_lib.load().mrb_gemm_tc_image_bytes(K, N) + 255) & ~255
+    return v
+
+
+class _ImageRef:
+    """A packed weight image inside a PackPlan buffer: address + a reference that keeps the buffer alive (what ``_lib.ptr``
+    needs of a tensor, without the cost of a tensor view per image on the launching thread)."""
+    __slots__ = ("addr", "owner")
+    is_cuda = True
+
+    def __init__(self, addr: int, owner: Tensor):
+        self.addr, self.owner = addr, owner
+
+    def data_ptr(self) -> int:
+        return self.addr
+
+    def is_contiguous(self) -> bool:
+        return True
 
 
 class PackPlan:
@@ -514,12 +538,11 @@ class PackPlan:
         self._asked, self._images, self._tex_asked, self._tex_out, self._pending = {}, {}, {}, {}, None
         if not reqs:
             return
-        lib = _lib.load()
         dev = reqs[0][0].device
         sizes, total = [], 0
         for (w0, w1, row, K, D, want_bwd) in reqs:
-            nf = (lib.mrb_gemm_tc_image_bytes(K, 2 * D) + 255) & ~255
-            nb = ((lib.mrb_gemm_tc_image_bytes(2 * D, K) + 255) & ~255) if want_bwd else 0
+            nf = _image_bytes(K, 2 * D)
+            nb = _image_bytes(2 * D, K) if want_bwd else 0
             sizes.append((total, nf, nb))
             total += nf + nb
         buf = torch.empty(total, dtype=torch.uint8, device=dev)
@@ -534,7 +557,8 @@ class PackPlan:
         _lib.call("mrb_gemm_tc_pack_graphconv_batch", n, *(ctypes.addressof(x) for x in (w0a, w1a, Ka, Da, fa, ba)))
         for r, (o, nf, nb) in zip(reqs, sizes):
             key = self._key(r[0], r[1], r[2], r[3], r[4])
-            self._images[key] = (buf[o:o + nf], buf[o + nf:o + nf + nb] if nb else None, r[0]._version, r[1]._version)
+            self._images[key] = (_ImageRef(base + o, buf), _ImageRef(base + o + nf, buf) if nb else None, r[0]._version,
+                                 r[1]._version)
         if EARLY_TEXEL_PROJECTION and fmap is not None and fmap.is_cuda and fmap.dim() == 4 and tex_keys:
             self._pending = (fmap, list(tex_keys))      # launched by ``launch_early`` (behind Cubify's count kernels)
 
@@ -1192,13 +1216,19 @@ def cached_face_cdf(owner, verts: Tensor, faces: Tensor, v_index: Sequence[int],
     return cdf
 
 
-def _next_seed() -> int:
-    # drawn from torch's CPU generator so that torch.manual_seed() makes sampling reproducible (no device sync); the rank is
-    # mixed in, so ranks that were seeded identically still draw different surface samples for their shards
-    s = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+def _next_seeds(n: int) -> List[int]:
+    """``n`` sampling seeds from torch's CPU generator (so that torch.manual_seed() makes sampling reproducible, no device
+    sync) in ONE draw -- the same values as ``n`` single draws (tests/test_host_logic.py), at a sixth of the host time.  The
+    rank is mixed in, so ranks that were seeded identically still draw different surface samples for their shards."""
+    seeds = torch.randint(0, 2 ** 62, (n,), dtype=torch.int64).tolist()
     if torch.distributed.is_available() and torch.distributed.is_initialized():
-        s ^= (torch.distributed.get_rank() * 0x9E3779B97F4A7C15) & (2 ** 62 - 1)
-    return s
+        mix = (torch.distributed.get_rank() * 0x9E3779B97F4A7C15) & (2 ** 62 - 1)
+        seeds = [s ^ mix for s in seeds]
+    return seeds
+
+
+def _next_seed() -> int:
+    return _next_seeds(1)[0]
 
 
 def sample_points(verts: Tensor, faces: Tensor, v_index: Sequence[int], f_index: Sequence[int], n: int,

@@ -85,7 +85,7 @@ class RefinementHead(nn.Module):
             # generator here, in the order the lazy path would take them (stage by stage: predicted cloud, GT cloud), so the
             # draws are the ones batched_mesh_loss(positions, ...) would make after the same torch.manual_seed.
             n_stage = len(self.refineStages)
-            seeds = [F_._next_seed() for _ in range(2 * n_stage)]
+            seeds = F_._next_seeds(2 * n_stage)
             loss_randomness = [({"seed": seeds[2 * s]}, {"seed": seeds[2 * s + 1]}) for s in range(n_stage)]
             gt_clouds = []
             F_.defer_until_stall(lambda: gt_clouds.extend(sample_gt_cloud(targets, **loss_randomness[s][1])

@@ -206,6 +206,17 @@ def test_world_size_2_gloo_gradient_allreduce(tmp_path):
     assert r.stdout.count("ok") == 2
 
 
+def test_batched_seed_draw_equals_single_draws():
+    """functional._next_seeds(n): one randint call, the values of n single draws (the refinement head pre-draws the seeds of all
+    stages; the lazy path draws them one by one)."""
+    from meshrcnn_b200.functional import _next_seed, _next_seeds
+    torch.manual_seed(77)
+    single = [_next_seed() for _ in range(6)] + [_next_seed()]
+    torch.manual_seed(77)
+    batched = _next_seeds(6) + [_next_seed()]
+    assert single == batched and len(set(single)) == 7
+
+
 def test_bench_reference_arm_extra_ranks_exit_quietly():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
